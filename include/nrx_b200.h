@@ -1,0 +1,128 @@
+/* nrx_b200.h — C ABI of the B200-native neural-receiver engine (libnrx_b200.so).
+ *
+ * The reference (theshubh007/neural_rx) has no FFI layer: its receiver boundary is the Python
+ * object API of utils/neural_rx.py.  Each entry point below states which reference interface it
+ * stands in for; the Python mirror classes in neural_rx_b200/receiver.py bind them with ctypes
+ * (see INTEGRATION.md).  Plain pointers and sizes only; every function returns an int status
+ * (0 = NRX_OK) and never throws; nrx_last_error() gives the message of the last failure on the
+ * calling thread.
+ *
+ * Tensor conventions (all row-major, last index fastest):
+ *   y            [B][1][N_rx][T][F]      complex64 (interleaved re,im)  — the `y` of
+ *                                         NeuralPUSCHReceiver.forward, utils/neural_rx.py:1544-1603
+ *   active_tx    [B][U]                   float32 0/1                   — `active_tx`, same call
+ *   llr          [B][U][n_data_res*bits]  float32, llr > 0 <=> bit 1    — CGNNOFDM.forward output,
+ *                                         utils/neural_rx.py:843-858,881 (RG-demapped, bit fastest)
+ *   llr_grid     [B][U][F][T][bits]       float32                       — CGNN.forward output,
+ *                                         utils/neural_rx.py:582-592
+ *   h_hat_ref    [B][U][F][T][2*N_rx]     float32 (re | im)             — ReadoutChEst, :593
+ *   h_hat_ls     [B][U][F][T][2*N_rx]     float32 (re | im)             — estimate_channel, :1462-1514
+ */
+#ifndef NRX_B200_H
+#define NRX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRX_OK 0
+#define NRX_ERR_INVALID 1      /* bad argument / shape mismatch (reference: assert / ValueError)   */
+#define NRX_ERR_UNSUPPORTED 2  /* architecture outside what the kernels implement
+                                  (reference: NotImplementedError("Unknown layer_type selected."))  */
+#define NRX_ERR_CUDA 3         /* CUDA runtime failure; message holds cudaGetErrorString            */
+#define NRX_ERR_WORKSPACE 4    /* caller workspace too small                                        */
+
+#define NRX_MAX_IO 4           /* StateInit / ReadoutLLRs stacks (one per MCS in Var-IO mode)       */
+#define NRX_MAX_DMRS 4
+#define NRX_MAX_TX 4
+
+typedef struct nrx_engine nrx_engine;
+
+/* What CGNN.__init__ / CGNNOFDM.__init__ read from sys_parameters
+ * (utils/neural_rx.py:407-530, 638-662) plus the PUSCH grid geometry. */
+typedef struct nrx_model_desc {
+    int32_t num_rx_ant;          /* N_rx (<= 7)                                                     */
+    int32_t max_num_tx;          /* U   (<= NRX_MAX_TX)                                             */
+    int32_t num_subcarriers;     /* F = 12 * n_size_bwp                                             */
+    int32_t num_ofdm_symbols;    /* T (14)                                                          */
+    int32_t d_s;                 /* state width (<= 64; 56 in all shipped configs)                  */
+    int32_t num_it;              /* number of CGNNIt blocks in the weight file                      */
+    int32_t units_init[2];       /* num_units_init   — must be {128,128}                            */
+    int32_t units_agg;           /* num_units_agg[i] — one hidden layer, <= 64                      */
+    int32_t units_state[2];      /* num_units_state[i] — must be {128,128}                          */
+    int32_t units_readout;       /* num_units_readout — one hidden layer of 128                     */
+    int32_t n_io;                /* number of StateInit / ReadoutLLRs stacks in the file            */
+    int32_t io_bits[NRX_MAX_IO]; /* output width of each LLR head (<= 8)                            */
+    int32_t num_dmrs_symbols;
+    int32_t dmrs_symbols[NRX_MAX_DMRS];
+    int32_t focc_block;          /* 2 * num_cdm_groups_without_data                                 */
+    int32_t num_data_res;        /* data REs per UE (RG demapper output length / bits)              */
+} nrx_model_desc;
+
+/* Replaces: building CGNNOFDM + `load_weights(model, path)` (utils/utils.py:53-70,
+ * scripts/evaluate.py:185-187).  `weight_arrays` is the unpickled Keras get_weights() list in
+ * file order (fp32, host memory), `weight_sizes[i]` its element counts; it is validated against
+ * `desc` exactly like set_weights would.  Geometry tables (host memory):
+ *   pilots     [U][n_dmrs*F][2]  float32  pilot_pattern.pilots (zeros off-comb)
+ *   nn_index   [U][T*F]          int32    nearest-pilot gather (utils/neural_rx.py:973-992)
+ *   pos_enc    [U][F][T][2]      float32  positional encoding (utils/onnx_utils.py:172-260)
+ *   data_index [T*F]             int32    ordinal among data REs or -1 (RG demapper)
+ * The engine copies everything to `device`; nothing is retained from the host pointers. */
+int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays,
+               const int64_t* weight_sizes, int32_t num_arrays, const float* pilots,
+               const int32_t* nn_index, const float* pos_enc, const int32_t* data_index,
+               int32_t device, nrx_engine** out);
+
+int nrx_destroy(nrx_engine* e);
+
+/* Replaces: the `num_it` property setter (utils/neural_rx.py:532-542): 1 <= n <= len(iterations),
+ * otherwise NRX_ERR_INVALID "Invalid number of iterations". */
+int nrx_set_num_it(nrx_engine* e, int32_t num_it);
+int nrx_get_num_it(const nrx_engine* e, int32_t* num_it);
+
+/* Slots pushed through all layers together (activations of one group stay L2-resident).
+ * 0 = whole batch in one pass. */
+int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
+
+/* Bytes of device scratch nrx_forward needs for `batch` slots. */
+int nrx_workspace_bytes(const nrx_engine* e, int32_t batch, size_t* bytes);
+
+/* Replaces: NeuralPUSCHReceiver.estimate_channel + CGNNOFDM.forward inference branch
+ * (utils/neural_rx.py:1462-1514, 813-881; CGNN.forward :544-595).  All pointers are DEVICE
+ * pointers owned by the caller; the call only enqueues work on `cuda_stream` (a cudaStream_t).
+ *   io_index   [B][U] int32 or NULL: StateInit stack per UE (the one-hot mcs_ue_mask, :562-569);
+ *              NULL = stack `llr_head` for every UE (mcs_ue_mask_eval=None, :818-823)
+ *   head_index [B][U] int32 or NULL: LLR readout head per UE; NULL = head `llr_head` for every
+ *              UE (the reference behaviour: only mcs_arr_eval[0] is evaluated, :847-858)
+ *   out_bits   values written per RE (<= 8): io_bits[llr_head] normally, fewer in masking mode
+ *   llr / llr_grid / h_hat_refined / h_hat_ls: outputs, any may be NULL (not written).        */
+int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y,
+                const float* active_tx, const int32_t* io_index, const int32_t* head_index,
+                int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
+                float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes);
+
+/* Same call with HOST buffers (pageable or pinned): stages through engine-owned pinned memory,
+ * copies host->device, runs, copies the requested outputs back and synchronises.  This is the
+ * call a drop-in user of the reference's receiver makes with NumPy arrays. */
+int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* active_tx,
+                     const int32_t* io_index, const int32_t* head_index, int32_t llr_head,
+                     int32_t out_bits, float* llr, float* llr_grid, float* h_hat_refined,
+                     float* h_hat_ls);
+
+/* Number of kernels nrx_forward enqueues for `batch` slots with the current settings. */
+int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launches);
+
+/* Algorithmic multiply-accumulates per user resource element for head `llr_head` at the current
+ * num_it (sum of weight elements, biases excluded — SURVEY.md App. A.6). */
+int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);
+
+const char* nrx_last_error(void);
+const char* nrx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRX_B200_H */

@@ -1,0 +1,377 @@
+"""CPU oracle for the neural-receiver hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module; the product (``neural_rx_b200``) never does.
+
+PARITY UNPINNED at LLR level: the reference ships no golden LLR vectors, no fixtures and no
+evaluation seeds, and its own implementation cannot run here (TensorFlow and
+Sionna are absent; the fork's torch port is broken).  This file is therefore a
+plain restatement of the *original TF semantics*, each function citing the reference lines it
+follows.  What *is* pinned against reference artefacts (tests/test_oracle_pins.py): weight-list
+layout and parameter counts for every shipped ``weights/*_weights`` file
+(``notebooks/nrx_architecture.ipynb:257,295-308,382``), I/O shapes of the TensorRT bindings
+(``notebooks/real_time_nrx.ipynb`` cell 6/16), the PUSCH geometry dump
+(``notebooks/jumpstart_tutorial.ipynb`` cell 17) and behavioural sanity (uncoded BER with the
+shipped weights).
+
+Everything is written with PyTorch CPU tensors (fp32 like ``nrx_dtype``; fp64 selectable) in the
+reference's own tensor conventions (channels-last ``[.., F, T, C]``, real parts then imaginary
+parts).  Third-party arithmetic that the reference delegates to ``sionna==0.18.0``
+(``PUSCHLSChannelEstimator``, ``NearestNeighborInterpolator``, ``ResourceGridDemapper``) is restated
+from its published behaviour and anchored on the in-tree twins cited below.
+"""
+from __future__ import annotations
+
+import dataclasses
+import pickle
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F_
+
+
+# --------------------------------------------------------------------------------------------
+# architecture description (what CGNN.__init__ reads from sys_parameters, utils/neural_rx.py:407-530)
+# --------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class OracleArch:
+    num_rx_ant: int = 4
+    d_s: int = 56
+    num_it: int = 2
+    num_units_init: Sequence[int] = (128, 128)
+    num_units_agg: Sequence[Sequence[int]] = ((64,), (64,))
+    num_units_state: Sequence[Sequence[int]] = ((128, 128), (128, 128))
+    num_units_readout: Sequence[int] = (128,)
+    num_bits_per_symbol: Sequence[int] = (4,)   # one entry per supported MCS
+    var_mcs_masking: bool = False
+    with_chest: bool = True
+
+    @property
+    def n_io(self) -> int:
+        return 1 if self.var_mcs_masking else len(self.num_bits_per_symbol)
+
+
+def load_weight_list(path: str) -> List[np.ndarray]:
+    """utils/utils.py:53-70 — the file is ``pickle.dump(model.get_weights())``."""
+    with open(path, "rb") as f:
+        return [np.asarray(a) for a in pickle.load(f)]
+
+
+class _Walker:
+    """Consumes the flat Keras list in creation order."""
+
+    def __init__(self, arrays, dtype):
+        self.a = list(arrays)
+        self.i = 0
+        self.dtype = dtype
+
+    def sep(self, cin, cout):
+        dw, pw, b = self.a[self.i:self.i + 3]
+        self.i += 3
+        assert dw.shape == (3, 3, cin, 1) and pw.shape == (1, 1, cin, cout) and b.shape == (cout,), \
+            (self.i, dw.shape, pw.shape, b.shape, cin, cout)
+        t = lambda x: torch.as_tensor(np.asarray(x), dtype=self.dtype)
+        return ("sep", t(dw[..., 0]), t(pw[0, 0]), t(b))
+
+    def dense(self, cin, cout):
+        k, b = self.a[self.i:self.i + 2]
+        self.i += 2
+        assert k.shape == (cin, cout) and b.shape == (cout,), (self.i, k.shape, b.shape, cin, cout)
+        t = lambda x: torch.as_tensor(np.asarray(x), dtype=self.dtype)
+        return ("dense", t(k), t(b))
+
+
+def bind_weights(arch: OracleArch, arrays, dtype=torch.float32):
+    w = _Walker(arrays, dtype)
+    cin0 = 2 * arch.num_rx_ant + 2 + (2 * arch.num_rx_ant if arch.with_chest else 0)
+    net = {"init": [], "it": [], "llr": [], "chest": None}
+    for _ in range(arch.n_io):
+        cin, stack = cin0, []
+        for n in list(arch.num_units_init) + [arch.d_s]:
+            stack.append(w.sep(cin, n))
+            cin = n
+        net["init"].append(stack)
+    for i in range(arch.num_it):
+        cin, agg = arch.d_s, []
+        for n in list(arch.num_units_agg[i]) + [arch.d_s]:
+            agg.append(w.dense(cin, n))
+            cin = n
+        cin, upd = 2 * arch.d_s + 2, []
+        for n in list(arch.num_units_state[i]) + [arch.d_s]:
+            upd.append(w.sep(cin, n))
+            cin = n
+        net["it"].append((agg, upd))
+    bits_heads = [max(arch.num_bits_per_symbol)] if arch.var_mcs_masking else list(arch.num_bits_per_symbol)
+    for bits in bits_heads:
+        cin, head = arch.d_s, []
+        for n in list(arch.num_units_readout) + [bits]:
+            head.append(w.dense(cin, n))
+            cin = n
+        net["llr"].append(head)
+    cin, head = arch.d_s, []
+    for n in list(arch.num_units_readout) + [2 * arch.num_rx_ant]:
+        head.append(w.dense(cin, n))
+        cin = n
+    net["chest"] = head
+    assert w.i == len(w.a), f"{len(w.a)} arrays in file, architecture consumes {w.i}"
+    return net
+
+
+# --------------------------------------------------------------------------------------------
+# precision emulation of the B200 engine (fp16 tensor-core operands, fp32 accumulate)
+# --------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Emulation:
+    """Where the CUDA engine rounds; all False/None == exact reference arithmetic."""
+    act_fp16: bool = False        # activations entering a depthwise conv / GEMM are fp16
+    weight_fp16: bool = False     # pointwise / dense kernels are fp16
+    dw_weight_fp16: bool = False  # depthwise taps are fp16
+    dw_acc_fp16: bool = False     # depthwise accumulates tap by tap in fp16 (HFMA2)
+    state_fp16: bool = False      # residual state s is carried in fp16
+
+    def q(self, x):
+        return x.half().to(x.dtype) if self.act_fp16 else x
+
+    def qw(self, w):
+        return w.half().to(w.dtype) if self.weight_fp16 else w
+
+    def qdw(self, w):
+        return w.half().to(w.dtype) if self.dw_weight_fp16 else w
+
+    def qs(self, s):
+        return s.half().to(s.dtype) if self.state_fp16 else s
+
+
+EXACT = Emulation()
+
+
+# --------------------------------------------------------------------------------------------
+# layers (Keras SeparableConv2D / Dense semantics)
+# --------------------------------------------------------------------------------------------
+def sepconv(x, layer, relu: bool, emu: Emulation = EXACT):
+    """x [N, F, T, Cin] -> [N, F, T, Cout].  depthwise 3x3 cross-correlation with zero 'same'
+    padding over (H = F, W = T), no depthwise bias; pointwise 1x1 + bias (+ ReLU)
+    (intent: ``utils/neural_rx copy_pytorch.py:34-51``; kernel layout App. A.2)."""
+    _, dw, pw, b = layer
+    x = emu.q(x)
+    dw = emu.qdw(dw)
+    xn = x.permute(0, 3, 1, 2)                                  # [N, C, F, T]
+    if emu.dw_acc_fp16:
+        xp = F_.pad(xn, (1, 1, 1, 1))
+        acc = torch.zeros_like(xn)
+        Fh, Tw = xn.shape[2], xn.shape[3]
+        for i in range(3):
+            for j in range(3):
+                acc = (acc + xp[:, :, i:i + Fh, j:j + Tw] * dw[i, j][None, :, None, None]).half().to(x.dtype)
+        d = acc
+    else:
+        wd = dw.permute(2, 0, 1)[:, None]                       # [C, 1, 3, 3]
+        d = F_.conv2d(xn, wd, padding=1, groups=xn.shape[1])
+    d = emu.q(d.permute(0, 2, 3, 1))
+    o = d @ emu.qw(pw) + b
+    return torch.relu(o) if relu else o
+
+
+def dense(x, layer, relu: bool, emu: Emulation = EXACT):
+    _, k, b = layer
+    o = emu.q(x) @ emu.qw(k) + b
+    return torch.relu(o) if relu else o
+
+
+# --------------------------------------------------------------------------------------------
+# CGNN forward (utils/neural_rx.py:544-595; TF-faithful draft copy_pytorch.py:470-514)
+# --------------------------------------------------------------------------------------------
+def cgnn_forward(net, arch: OracleArch, y, pe, h_hat, active_tx, mcs_ue_mask,
+                 num_it: Optional[int] = None, emu: Emulation = EXACT):
+    """y [B,F,T,2N]; pe [U,F,T,2]; h_hat [B,U,F,T,2N]; active_tx [B,U]; mcs_ue_mask [B,U,n_mcs].
+    Returns (llrs: list over MCS heads of [B,U,F,T,bits], h_refined [B,U,F,T,2N]) of the last
+    iteration (inference branch, :582-593)."""
+    num_it = arch.num_it if num_it is None else num_it
+    assert 1 <= num_it <= arch.num_it, "Invalid number of iterations"        # :539-541
+    B, U = y.shape[0], pe.shape[0]
+    # normalisation (:551-557): one scalar per batch sample
+    g = torch.rsqrt(torch.mean(y * y, dim=(1, 2, 3), keepdim=True))
+    g = torch.where(torch.isfinite(g), g, torch.zeros_like(g))               # divide_no_nan in the TF original
+    y = y * g
+    h_hat = h_hat * g[:, None]
+    # StateInit (:107-132): tile y over users, tile pe over batch, concat [y, pe, h_hat]
+    yt = y[:, None].expand(B, U, *y.shape[1:]).reshape(B * U, *y.shape[1:])
+    pet = pe[None].expand(B, *pe.shape).reshape(B * U, *pe.shape[1:])
+    z0 = torch.cat([yt, pet, h_hat.reshape(B * U, *h_hat.shape[2:])], dim=-1)
+
+    def run_stack(z, stack):
+        for l in stack[:-1]:
+            z = sepconv(z, l, True, emu)
+        return sepconv(z, stack[-1], False, emu)
+
+    if arch.var_mcs_masking:
+        s = run_stack(z0, net["init"][0])
+    else:                                                                     # :562-569
+        s = 0
+        for m, stack in enumerate(net["init"]):
+            sm = run_stack(z0, stack).reshape(B, U, *z0.shape[1:3], arch.d_s)
+            s = s + sm * mcs_ue_mask[:, :, m][:, :, None, None, None]
+        s = s.reshape(B * U, *z0.shape[1:3], arch.d_s)
+    s = emu.qs(s)
+
+    act = active_tx[:, :, None, None, None]
+    for i in range(num_it):
+        agg, upd = net["it"][i]
+        # AggregateUserStates (:176-207)
+        sp = s
+        for l in agg[:-1]:
+            sp = dense(sp, l, True, emu)
+        sp = dense(sp, agg[-1], False, emu)
+        sp = sp.reshape(B, U, *sp.shape[1:]) * act
+        a = sp.sum(dim=1, keepdim=True) - sp
+        p = torch.relu(active_tx.sum(dim=1, keepdim=True) - 1.0)
+        p = torch.where(p == 0.0, torch.ones_like(p), 1.0 / torch.clamp(p, min=1e-10))
+        a = (a * p[:, :, None, None, None]).reshape(B * U, *sp.shape[2:])
+        # UpdateState (:249-270): concat [a, s, pe], sep-conv stack, skip connection
+        z = torch.cat([a, s, pet], dim=-1)
+        s = emu.qs(s + run_stack(z, upd))
+
+    llrs = []
+    for m in range(len(arch.num_bits_per_symbol)):
+        head = net["llr"][0] if arch.var_mcs_masking else net["llr"][m]
+        o = s
+        for l in head[:-1]:
+            o = dense(o, l, True, emu)
+        o = dense(o, head[-1], False, emu)
+        if arch.var_mcs_masking:
+            o = o[..., :arch.num_bits_per_symbol[m]]                          # :586-588
+        llrs.append(o.reshape(B, U, *o.shape[1:]))
+    o = s
+    for l in net["chest"][:-1]:
+        o = dense(o, l, True, emu)
+    h_ref = dense(o, net["chest"][-1], False, emu)
+    return llrs, h_ref.reshape(B, U, *h_ref.shape[1:])
+
+
+# --------------------------------------------------------------------------------------------
+# PUSCH geometry restated generically (any pilot pattern), loops as in the reference
+# --------------------------------------------------------------------------------------------
+def nn_gather_indices(pilots: np.ndarray, pilot_mask: np.ndarray) -> np.ndarray:
+    """Nearest-neighbour interpolation indices, one row per transmitter.
+
+    pilots [U, n_p] complex; pilot_mask [T, F] bool (same mask for every tx, as in PUSCH).
+    For every RE the non-zero-energy pilot with the smallest Manhattan distance is taken,
+    ``np.argmin`` tie-break = lowest pilot index (``utils/neural_rx.py:973-992``).  -> [U, T*F]."""
+    T, Fs = pilot_mask.shape
+    i_p, j_p = np.where(pilot_mask)
+    out = np.zeros((pilots.shape[0], T * Fs), dtype=np.int32)
+    big = T + Fs
+    for u in range(pilots.shape[0]):
+        zero = np.abs(pilots[u]) == 0
+        for i in range(T):
+            d = np.abs(i - i_p)[None, :] + np.abs(np.arange(Fs)[:, None] - j_p[None, :])
+            d[:, zero] = big
+            out[u, i * Fs:(i + 1) * Fs] = np.argmin(d, axis=1)
+    return out
+
+
+def positional_encoding(pilots: np.ndarray, pilot_mask: np.ndarray) -> np.ndarray:
+    """utils/onnx_utils.py:172-260 — distance to the nearest own pilot (|pilot| > 1e-3) in time
+    and in frequency, each centred and scaled by its population std along its own axis.
+    -> [U, F, T, 2] float32 (time, freq)."""
+    T, Fs = pilot_mask.shape
+    i_p, j_p = np.where(pilot_mask)
+    U = pilots.shape[0]
+    dist_t = np.zeros((U, T, Fs))
+    dist_f = np.zeros((U, T, Fs))
+    for u in range(U):
+        sel = np.abs(pilots[u]) > 1e-3
+        tp, fp = i_p[sel], j_p[sel]
+        dist_t[u] = np.min(np.abs(tp[None, :] - np.arange(T)[:, None]), axis=1)[:, None]
+        dist_f[u] = np.min(np.abs(fp[None, :] - np.arange(Fs)[:, None]), axis=1)[None, :]
+    dist_t -= np.mean(dist_t, axis=1, keepdims=True)
+    std = np.std(dist_t, axis=1, keepdims=True)
+    dist_t = np.where(std > 0., dist_t / np.where(std > 0., std, 1.), dist_t)
+    dist_f -= np.mean(dist_f, axis=2, keepdims=True)
+    std = np.std(dist_f, axis=2, keepdims=True)
+    dist_f = np.where(std > 0., dist_f / np.where(std > 0., std, 1.), dist_f)
+    pe = np.stack([dist_t, dist_f], axis=-1).astype(np.float32)              # [U, T, F, 2]
+    return np.transpose(pe, (0, 2, 1, 3))
+
+
+def ls_channel_estimate(y: np.ndarray, pilots: np.ndarray, pilot_mask: np.ndarray,
+                        num_cdm_groups_without_data: int = 2,
+                        nn_index: Optional[np.ndarray] = None) -> np.ndarray:
+    """``PUSCHLSChannelEstimator(..., interpolation_type="nn")([y, no])`` followed by the slicing of
+    ``NeuralPUSCHReceiver.estimate_channel`` (``copy_pytorch.py:899-911``).
+
+    y [B, 1, N_rx, T, F] complex -> h_hat [B, U, F, T, 2*N_rx] float32 (re | im).
+      1. LS at pilot slots, safe division (``utils/neural_rx.py:1289-1294``)
+      2. FOCC / CDM de-spreading: mean of the two non-zero estimates in every block of
+         2*num_cdm_groups_without_data pilot slots, kept only where the raw estimate is non-zero
+         (in-tree twin ``utils/neural_rx.py:1620-1629``)
+      3. nearest-neighbour broadcast over the grid."""
+    B, _, N, T, Fs = y.shape
+    i_p, j_p = np.where(pilot_mask)
+    yp = y[:, 0][:, :, i_p, j_p]                                             # [B, N, n_p]
+    U = pilots.shape[0]
+    if nn_index is None:
+        nn_index = nn_gather_indices(pilots, pilot_mask)
+    n = 2 * num_cdm_groups_without_data
+    out = np.zeros((B, U, Fs, T, 2 * N), dtype=np.float32)
+    for u in range(U):
+        p = pilots[u]
+        nz = np.abs(p) > 0
+        h = np.zeros_like(yp)
+        h[..., nz] = yp[..., nz] / p[nz]
+        hb = h.reshape(B, N, -1, n)
+        cond = np.abs(hb) > 0
+        hs = np.repeat(hb.sum(axis=-1, keepdims=True) / 2.0, n, axis=-1)
+        h = np.where(cond, hs, 0).reshape(B, N, -1)
+        hg = h[..., nn_index[u]].reshape(B, N, T, Fs)                        # [B, N, T, F]
+        hg = np.transpose(hg, (0, 3, 2, 1))                                  # [B, F, T, N]
+        out[:, u] = np.concatenate([hg.real, hg.imag], axis=-1)
+    return out
+
+
+def preprocess_y(y: np.ndarray) -> np.ndarray:
+    """copy_pytorch.py:733-735 — ``y[:,0]``, permute(0,3,2,1), re|im  -> [B, F, T, 2*N_rx]."""
+    yy = np.transpose(y[:, 0], (0, 3, 2, 1))
+    return np.concatenate([yy.real, yy.imag], axis=-1).astype(np.float32)
+
+
+def demap_llrs(llr: np.ndarray, pilot_mask: np.ndarray) -> np.ndarray:
+    """``ResourceGridDemapper`` + flatten + single-layer ``LayerDemapper``
+    (copy_pytorch.py:755-766; ordering ``utils/onnx_utils.py:486-514``):
+    [B,U,F,T,bits] -> [B,U,T,F,bits] -> data REs in ascending flattened (t*F+f) order ->
+    (RE, bit) flattened, bit fastest."""
+    B, U, Fs, T, bits = llr.shape
+    x = np.transpose(llr, (0, 1, 3, 2, 4)).reshape(B, U, T * Fs, bits)
+    data_ind = np.argsort(pilot_mask.reshape(-1), kind="stable")[:int((~pilot_mask).sum())]
+    return x[:, :, data_ind, :].reshape(B, U, -1)
+
+
+def receiver_forward(net, arch: OracleArch, y, pilots, pilot_mask, active_tx,
+                     mcs_arr_eval=(0,), mcs_ue_mask_eval=None, num_it=None,
+                     dtype=torch.float32, emu: Emulation = EXACT, tables=None):
+    """``NeuralPUSCHReceiver.forward`` inference branch up to the LLRs
+    (``utils/neural_rx.py:1581-1603`` -> ``CGNNOFDM.forward`` ``:813-881``).
+
+    Returns dict(llr=[B,U,n_data*bits] of head mcs_arr_eval[0], llr_grid (all heads),
+    h_hat_refined=[B,U,F,T,2N], h_hat=[B,U,F,T,2N])."""
+    B = y.shape[0]
+    U = active_tx.shape[1]
+    if tables is None:
+        tables = dict(nn=nn_gather_indices(pilots, pilot_mask), pe=positional_encoding(pilots, pilot_mask))
+    h_hat = ls_channel_estimate(y, pilots[:U], pilot_mask, nn_index=tables["nn"][:U])
+    n_mcs = len(arch.num_bits_per_symbol)
+    if mcs_ue_mask_eval is None:                                             # :818-823
+        m = np.zeros((1, 1, n_mcs), np.float32)
+        m[..., mcs_arr_eval[0]] = 1.0
+        mask = np.broadcast_to(m, (B, U, n_mcs)).copy()
+    else:
+        mask = np.asarray(mcs_ue_mask_eval, np.float32).reshape(-1, U, n_mcs)
+        mask = np.broadcast_to(mask, (B, U, n_mcs)).copy()
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
+    with torch.no_grad():
+        llrs, h_ref = cgnn_forward(net, arch, t(preprocess_y(y)), t(tables["pe"][:U]), t(h_hat),
+                                   t(active_tx), t(mask), num_it=num_it, emu=emu)
+    llr_grid = [l.float().numpy() for l in llrs]
+    return dict(llr=demap_llrs(llr_grid[mcs_arr_eval[0]], pilot_mask), llr_grid=llr_grid,
+                h_hat_refined=h_ref.float().numpy(), h_hat=h_hat)
