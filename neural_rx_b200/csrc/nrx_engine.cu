@@ -1,0 +1,577 @@
+// nrx_engine.cu — host side of libnrx_b200.so: weight packing, workspace layout, launch sequence
+// and the C ABI declared in include/nrx_b200.h.
+//
+// build: see neural_rx_b200/build.py
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC ...
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nrx_b200.h"
+#include "nrx_kernels.cuh"
+
+using namespace nrx;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define NRX_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t err_ = (expr);                                                          \
+        if (err_ != cudaSuccess)                                                            \
+            return fail(NRX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(err_));    \
+    } while (0)
+
+struct SepLayer {          // one SeparableConv2D position of a stack (n_stacks copies for Var-IO)
+    uint8_t* blob = nullptr;
+    uint32_t blob_bytes = 0;
+    int kpad = 0, npad = 0, n_stacks = 1;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// fp16 K-major SWIZZLE_128B image of W^T: rows n (NPAD), slabs of 64 k.  kmap[c] = K index of input c.
+void pack_pw(uint8_t* img, const float* w, int cin, int cout, int npad, const std::vector<int>& kmap, int n_off = 0) {
+    for (int c = 0; c < cin; ++c)
+        for (int n = 0; n < cout; ++n) {
+            const int k = kmap[c], row = n + n_off;
+            *reinterpret_cast<__half*>(img + size_t(k / 64) * npad * 128 + sw128_offset(row, k % 64)) =
+                __float2half(w[size_t(c) * cout + n]);
+        }
+}
+
+}  // namespace
+
+struct nrx_engine {
+    nrx_model_desc d{};
+    int device = 0, num_sms = 148;
+    int num_it = 1, slots_per_pass = 0;
+    int cin0 = 0;                                   // 4N + 2
+    std::vector<SepLayer> init_layers;              // 3
+    std::vector<std::vector<SepLayer>> upd_layers;  // [it][3]
+    std::vector<uint8_t*> agg_blobs;                // [it]
+    uint8_t* readout_blob = nullptr;                // [n_io] heads
+    int32_t* nn_index = nullptr;
+    FoccEntry* focc = nullptr;
+    float* pos_enc = nullptr;
+    int32_t* data_index = nullptr;
+    int n_pilot_slots = 0;
+    int64_t mac_fixed[NRX_MAX_IO] = {0};            // StateInit + readouts per head
+    int64_t mac_per_it = 0;
+    // host-call staging (nrx_forward_host)
+    cudaStream_t stream = nullptr;
+    void* h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    void* d_io = nullptr;
+    size_t d_io_bytes = 0;
+    void* d_ws = nullptr;
+    size_t d_ws_bytes = 0;
+};
+
+namespace {
+
+struct Workspace {
+    size_t partial, z0, h1, h2, abuf, sbuf, total;
+};
+
+int pass_slots(const nrx_engine* e, int batch) {
+    int s = e->slots_per_pass <= 0 ? batch : e->slots_per_pass;
+    return s > batch ? batch : s;
+}
+
+Workspace layout(const nrx_engine* e, int batch) {
+    const size_t P = size_t(pass_slots(e, batch)) * e->d.max_num_tx * e->d.num_subcarriers * kT;
+    Workspace w{};
+    size_t off = 0;
+    w.partial = off; off = align_up(off + size_t(batch) * kPowerParts * 4, 256);
+    w.z0 = off;      off = align_up(off + P * 32 * 2, 256);
+    w.h1 = off;      off = align_up(off + P * 128 * 2, 256);
+    w.h2 = off;      off = align_up(off + P * 128 * 2, 256);
+    w.abuf = off;    off = align_up(off + P * 64 * 2, 256);
+    w.sbuf = off;    off = align_up(off + P * 64 * 2, 256);
+    w.total = off;
+    return w;
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// Build the device blob of one sep-conv layer position for all stacks.
+int build_sep_layer(SepLayer& L, int n_stacks, const float* const* arrays, const int64_t* sizes, int first,
+                    int stride, int cin, int cout, int kpad, int npad, const std::vector<int>& kmap) {
+    const int KS = (kpad + 63) / 64;
+    const uint32_t wpw = KS * npad * 128, wdw = 9 * kpad * 2, wb = npad * 4;
+    L.kpad = kpad;
+    L.npad = npad;
+    L.n_stacks = n_stacks;
+    L.blob_bytes = wpw + wdw + wb;
+    std::vector<uint8_t> host(size_t(L.blob_bytes) * n_stacks, 0);
+    for (int s = 0; s < n_stacks; ++s) {
+        const int i = first + s * stride;
+        if (sizes[i] != int64_t(9) * cin || sizes[i + 1] != int64_t(cin) * cout || sizes[i + 2] != cout)
+            return fail(NRX_ERR_INVALID, "SeparableConv2D(%d->%d) expected at weight index %d", cin, cout, i);
+        uint8_t* b = host.data() + size_t(s) * L.blob_bytes;
+        pack_pw(b, arrays[i + 1], cin, cout, npad, kmap);
+        __half* dw = reinterpret_cast<__half*>(b + wpw);
+        for (int tap = 0; tap < 9; ++tap)                      // [3][3][cin][1] -> [9][KPAD]
+            for (int c = 0; c < cin; ++c) dw[tap * kpad + kmap[c]] = __float2half(arrays[i][size_t(tap) * cin + c]);
+        float* bias = reinterpret_cast<float*>(b + wpw + wdw);
+        for (int n = 0; n < cout; ++n) bias[n] = arrays[i + 2][n];
+    }
+    NRX_CUDA(cudaMalloc(&L.blob, host.size()));
+    NRX_CUDA(cudaMemcpy(L.blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+    return NRX_OK;
+}
+
+std::vector<int> identity_map(int n) {
+    std::vector<int> m(n);
+    for (int i = 0; i < n; ++i) m[i] = i;
+    return m;
+}
+
+template <int KPAD, int NPAD, int MODE>
+void launch_sep(const nrx_engine* e, cudaStream_t st, SepParams p) {
+    const int grid = p.num_tiles < 2 * e->num_sms ? p.num_tiles : 2 * e->num_sms;
+    nrx_sepconv_kernel<KPAD, NPAD, MODE><<<grid, kThreads, SepSmem<KPAD, NPAD>::kTotal, st>>>(p);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nrx_last_error(void) { return g_last_error.c_str(); }
+const char* nrx_version(void) { return "nrx_b200 0.1 (sm_100a)"; }
+
+int nrx_destroy(nrx_engine* e) {
+    if (!e) return NRX_OK;
+    cudaSetDevice(e->device);
+    for (auto& L : e->init_layers) cudaFree(L.blob);
+    for (auto& it : e->upd_layers)
+        for (auto& L : it) cudaFree(L.blob);
+    for (auto* b : e->agg_blobs) cudaFree(b);
+    cudaFree(e->readout_blob);
+    cudaFree(e->nn_index);
+    cudaFree(e->focc);
+    cudaFree(e->pos_enc);
+    cudaFree(e->data_index);
+    cudaFree(e->d_io);
+    cudaFree(e->d_ws);
+    if (e->h_pin) cudaFreeHost(e->h_pin);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return NRX_OK;
+}
+
+int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, const int64_t* weight_sizes,
+               int32_t num_arrays, const float* pilots, const int32_t* nn_index, const float* pos_enc,
+               const int32_t* data_index, int32_t device, nrx_engine** out) {
+    if (!desc || !weight_arrays || !weight_sizes || !pilots || !nn_index || !pos_enc || !data_index || !out)
+        return fail(NRX_ERR_INVALID, "nrx_create: null argument");
+    const nrx_model_desc& d = *desc;
+    if (d.num_ofdm_symbols != kT) return fail(NRX_ERR_UNSUPPORTED, "only 14-symbol slots are implemented");
+    if (d.num_rx_ant < 1 || d.num_rx_ant > 7) return fail(NRX_ERR_UNSUPPORTED, "num_rx_ant must be in [1, 7]");
+    if (d.max_num_tx < 1 || d.max_num_tx > kAggMaxU) return fail(NRX_ERR_UNSUPPORTED, "max_num_tx must be in [1, 4]");
+    if (d.d_s < 4 || d.d_s > 60 || d.d_s % 4) return fail(NRX_ERR_UNSUPPORTED, "d_s must be a multiple of 4 in [4, 60]");
+    for (int i = 0; i < 2; ++i)
+        if (d.units_init[i] < 1 || d.units_init[i] > 128 || d.units_state[i] < 1 || d.units_state[i] > 128)
+            return fail(NRX_ERR_UNSUPPORTED, "hidden sep-conv widths must be <= 128");
+    if (d.units_agg < 1 || d.units_agg > 64) return fail(NRX_ERR_UNSUPPORTED, "units_agg must be <= 64");
+    if (d.units_readout < 1 || d.units_readout > 128) return fail(NRX_ERR_UNSUPPORTED, "units_readout must be <= 128");
+    if (d.n_io < 1 || d.n_io > NRX_MAX_IO) return fail(NRX_ERR_INVALID, "n_io out of range");
+    for (int m = 0; m < d.n_io; ++m)
+        if (d.io_bits[m] < 1 || d.io_bits[m] > 16) return fail(NRX_ERR_UNSUPPORTED, "LLR head width must be <= 16");
+    if (d.num_it < 1) return fail(NRX_ERR_INVALID, "num_it must be >= 1");
+    if (d.num_subcarriers < 1 || d.focc_block < 1 || d.num_subcarriers % d.focc_block)
+        return fail(NRX_ERR_INVALID, "num_subcarriers must be a positive multiple of focc_block");
+    if (d.num_dmrs_symbols < 1 || d.num_dmrs_symbols > NRX_MAX_DMRS) return fail(NRX_ERR_INVALID, "bad DMRS symbol count");
+    const int expected = d.n_io * 9 + d.num_it * (4 + 9) + d.n_io * 4 + 4;
+    if (num_arrays != expected)
+        return fail(NRX_ERR_INVALID, "weight list has %d arrays, architecture consumes %d", num_arrays, expected);
+
+    NRX_CUDA(cudaSetDevice(device));
+    nrx_engine* e = new nrx_engine();
+    e->d = d;
+    e->device = device;
+    e->num_it = d.num_it;
+    e->cin0 = 4 * d.num_rx_ant + 2;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->num_sms = prop.multiProcessorCount;
+
+    int rc = NRX_OK;
+    auto bail = [&](int code) { nrx_destroy(e); return code; };
+
+    // ---- StateInit stacks: per stack 3 sep-convs (9 arrays) ------------------------------------
+    const int widths_i[4] = {e->cin0, d.units_init[0], d.units_init[1], d.d_s};
+    e->init_layers.resize(3);
+    for (int l = 0; l < 3; ++l) {
+        const int kpad = l == 0 ? 32 : 128, npad = l == 2 ? 64 : 128;
+        rc = build_sep_layer(e->init_layers[l], d.n_io, weight_arrays, weight_sizes, 3 * l, 9, widths_i[l],
+                             widths_i[l + 1], kpad, npad, identity_map(widths_i[l]));
+        if (rc) return bail(rc);
+    }
+    for (int m = 0; m < d.n_io; ++m)
+        for (int l = 0; l < 3; ++l) e->mac_fixed[m] += int64_t(9 + widths_i[l + 1]) * widths_i[l];
+
+    // ---- iterations -----------------------------------------------------------------------------
+    int idx = d.n_io * 9;
+    std::vector<int> upd_map(2 * d.d_s + 2);
+    for (int c = 0; c < 2 * d.d_s + 2; ++c) upd_map[c] = c < d.d_s ? c : 64 + (c - d.d_s);   // [a | s, pe]
+    const int widths_u[4] = {2 * d.d_s + 2, d.units_state[0], d.units_state[1], d.d_s};
+    e->upd_layers.resize(d.num_it);
+    e->agg_blobs.resize(d.num_it, nullptr);
+    for (int it = 0; it < d.num_it; ++it) {
+        if (weight_sizes[idx] != int64_t(d.d_s) * d.units_agg || weight_sizes[idx + 1] != d.units_agg ||
+            weight_sizes[idx + 2] != int64_t(d.units_agg) * d.d_s || weight_sizes[idx + 3] != d.d_s)
+            return bail(fail(NRX_ERR_INVALID, "AggregateUserStates Dense layers expected at weight index %d", idx));
+        std::vector<uint8_t> host(kAggBlob, 0);
+        pack_pw(host.data(), weight_arrays[idx], d.d_s, d.units_agg, 64, identity_map(d.d_s));
+        pack_pw(host.data() + 8192, weight_arrays[idx + 2], d.units_agg, d.d_s, 64, identity_map(d.units_agg));
+        float* b1 = reinterpret_cast<float*>(host.data() + 16384);
+        for (int n = 0; n < d.units_agg; ++n) b1[n] = weight_arrays[idx + 1][n];
+        for (int n = 0; n < d.d_s; ++n) b1[64 + n] = weight_arrays[idx + 3][n];
+        if (cudaMalloc(&e->agg_blobs[it], kAggBlob) != cudaSuccess ||
+            cudaMemcpy(e->agg_blobs[it], host.data(), kAggBlob, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(NRX_ERR_CUDA, "uploading aggregation weights failed"));
+        idx += 4;
+        e->upd_layers[it].resize(3);
+        for (int l = 0; l < 3; ++l) {
+            const int npad = l == 2 ? 64 : 128;
+            rc = build_sep_layer(e->upd_layers[it][l], 1, weight_arrays, weight_sizes, idx, 0, widths_u[l],
+                                 widths_u[l + 1], 128, npad, l == 0 ? upd_map : identity_map(widths_u[l]));
+            if (rc) return bail(rc);
+            idx += 3;
+        }
+    }
+    e->mac_per_it = 2 * int64_t(d.d_s) * d.units_agg;
+    for (int l = 0; l < 3; ++l) e->mac_per_it += int64_t(9 + widths_u[l + 1]) * widths_u[l];
+
+    // ---- read-outs: n_io LLR heads then the channel-estimate head ------------------------------
+    {
+        const int ch = idx + 4 * d.n_io, n2 = 2 * d.num_rx_ant;
+        if (weight_sizes[ch] != int64_t(d.d_s) * d.units_readout || weight_sizes[ch + 1] != d.units_readout ||
+            weight_sizes[ch + 2] != int64_t(d.units_readout) * n2 || weight_sizes[ch + 3] != n2)
+            return bail(fail(NRX_ERR_INVALID, "ReadoutChEst Dense layers expected at weight index %d", ch));
+        std::vector<uint8_t> host(size_t(kRoBlob) * d.n_io, 0);
+        std::vector<int> k_llr = identity_map(d.units_readout), k_h(d.units_readout);
+        for (int c = 0; c < d.units_readout; ++c) k_h[c] = 128 + c;
+        for (int m = 0; m < d.n_io; ++m) {
+            const int i = idx + 4 * m, bits = d.io_bits[m];
+            if (weight_sizes[i] != int64_t(d.d_s) * d.units_readout || weight_sizes[i + 1] != d.units_readout ||
+                weight_sizes[i + 2] != int64_t(d.units_readout) * bits || weight_sizes[i + 3] != bits)
+                return bail(fail(NRX_ERR_INVALID, "ReadoutLLRs Dense layers expected at weight index %d", i));
+            uint8_t* b = host.data() + size_t(m) * kRoBlob;
+            pack_pw(b, weight_arrays[i], d.d_s, d.units_readout, 256, identity_map(d.d_s), 0);
+            pack_pw(b, weight_arrays[ch], d.d_s, d.units_readout, 256, identity_map(d.d_s), 128);
+            pack_pw(b + kRoW1, weight_arrays[i + 2], d.units_readout, bits, 32, k_llr, 0);
+            pack_pw(b + kRoW1, weight_arrays[ch + 2], d.units_readout, n2, 32, k_h, 16);
+            float* b1 = reinterpret_cast<float*>(b + kRoW1 + kRoW2);
+            for (int n = 0; n < d.units_readout; ++n) {
+                b1[n] = weight_arrays[i + 1][n];
+                b1[128 + n] = weight_arrays[ch + 1][n];
+            }
+            float* b2 = b1 + 256;
+            for (int n = 0; n < bits; ++n) b2[n] = weight_arrays[i + 3][n];
+            for (int n = 0; n < n2; ++n) b2[16 + n] = weight_arrays[ch + 3][n];
+            e->mac_fixed[m] += int64_t(d.d_s) * d.units_readout * 2 + int64_t(d.units_readout) * (bits + n2);
+        }
+        if (cudaMalloc(&e->readout_blob, host.size()) != cudaSuccess ||
+            cudaMemcpy(e->readout_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(NRX_ERR_CUDA, "uploading read-out weights failed"));
+    }
+
+    // ---- geometry tables ----------------------------------------------------------------------
+    const int F = d.num_subcarriers, U = d.max_num_tx, TF = kT * F;
+    e->n_pilot_slots = d.num_dmrs_symbols * F;
+    {
+        // FOCC / CDM de-spreading table: the estimate of pilot slot k is the sum over the non-zero
+        // pilots of its block of focc_block consecutive slots of y/p, divided by 2
+        // (twin in the reference: utils/neural_rx.py:1620-1629).
+        std::vector<FoccEntry> tab(size_t(U) * e->n_pilot_slots);
+        for (int u = 0; u < U; ++u)
+            for (int k = 0; k < e->n_pilot_slots; ++k) {
+                FoccEntry en{};
+                const float* pk = pilots + (size_t(u) * e->n_pilot_slots + k) * 2;
+                if (pk[0] != 0.f || pk[1] != 0.f) {
+                    const int b0 = k / d.focc_block * d.focc_block;
+                    int n = 0;
+                    for (int j = b0; j < b0 + d.focc_block; ++j) {
+                        const float* pj = pilots + (size_t(u) * e->n_pilot_slots + j) * 2;
+                        const float mag = pj[0] * pj[0] + pj[1] * pj[1];
+                        if (mag == 0.f) continue;
+                        if (n >= 2) return bail(fail(NRX_ERR_UNSUPPORTED, "more than two pilots per FOCC block"));
+                        en.src[n] = d.dmrs_symbols[j / F] * F + j % F;
+                        en.w[n] = make_float2(0.5f * pj[0] / mag, -0.5f * pj[1] / mag);   // 0.5 / p
+                        ++n;
+                    }
+                }
+                tab[size_t(u) * e->n_pilot_slots + k] = en;
+            }
+        for (int u = 0; u < U; ++u)
+            for (int i = 0; i < TF; ++i) {
+                const int k = nn_index[size_t(u) * TF + i];
+                if (k < 0 || k >= e->n_pilot_slots) return bail(fail(NRX_ERR_INVALID, "nn_index out of range"));
+            }
+        if (cudaMalloc(&e->focc, tab.size() * sizeof(FoccEntry)) != cudaSuccess ||
+            cudaMemcpy(e->focc, tab.data(), tab.size() * sizeof(FoccEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&e->nn_index, size_t(U) * TF * 4) != cudaSuccess ||
+            cudaMemcpy(e->nn_index, nn_index, size_t(U) * TF * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&e->pos_enc, size_t(U) * TF * 2 * 4) != cudaSuccess ||
+            cudaMemcpy(e->pos_enc, pos_enc, size_t(U) * TF * 2 * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&e->data_index, size_t(TF) * 4) != cudaSuccess ||
+            cudaMemcpy(e->data_index, data_index, size_t(TF) * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(NRX_ERR_CUDA, "uploading geometry tables failed"));
+    }
+
+    // ---- kernel attributes ---------------------------------------------------------------------
+    cudaError_t ce = cudaSuccess;
+    auto acc = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+    acc(set_smem(nrx_sepconv_kernel<32, 128, kHidden>, SepSmem<32, 128>::kTotal));
+    acc(set_smem(nrx_sepconv_kernel<128, 128, kHidden>, SepSmem<128, 128>::kTotal));
+    acc(set_smem(nrx_sepconv_kernel<128, 64, kInitOut>, SepSmem<128, 64>::kTotal));
+    acc(set_smem(nrx_sepconv_kernel<128, 64, kUpdateOut>, SepSmem<128, 64>::kTotal));
+    acc(set_smem(nrx_agg_kernel<1>, agg_smem_bytes(1)));
+    acc(set_smem(nrx_agg_kernel<2>, agg_smem_bytes(2)));
+    acc(set_smem(nrx_agg_kernel<3>, agg_smem_bytes(3)));
+    acc(set_smem(nrx_agg_kernel<4>, agg_smem_bytes(4)));
+    acc(set_smem(nrx_readout_kernel, kRoSmem));
+    if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
+    NRX_CUDA(cudaDeviceSynchronize());
+    *out = e;
+    return NRX_OK;
+}
+
+int nrx_set_num_it(nrx_engine* e, int32_t num_it) {
+    if (!e) return fail(NRX_ERR_INVALID, "null engine");
+    if (num_it < 1 || num_it > e->d.num_it) return fail(NRX_ERR_INVALID, "Invalid number of iterations");
+    e->num_it = num_it;
+    return NRX_OK;
+}
+
+int nrx_get_num_it(const nrx_engine* e, int32_t* num_it) {
+    if (!e || !num_it) return fail(NRX_ERR_INVALID, "null argument");
+    *num_it = e->num_it;
+    return NRX_OK;
+}
+
+int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots) {
+    if (!e || slots < 0) return fail(NRX_ERR_INVALID, "slots_per_pass must be >= 0");
+    e->slots_per_pass = slots;
+    return NRX_OK;
+}
+
+int nrx_workspace_bytes(const nrx_engine* e, int32_t batch, size_t* bytes) {
+    if (!e || !bytes || batch < 1) return fail(NRX_ERR_INVALID, "nrx_workspace_bytes: bad argument");
+    *bytes = layout(e, batch).total;
+    return NRX_OK;
+}
+
+int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launches) {
+    if (!e || !launches || batch < 1) return fail(NRX_ERR_INVALID, "nrx_launches_per_forward: bad argument");
+    const int bp = pass_slots(e, batch);
+    const int passes = (batch + bp - 1) / bp;
+    *launches = 1 + passes * (1 + 3 + e->num_it * 4 + 1);
+    return NRX_OK;
+}
+
+int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs) {
+    if (!e || !macs || llr_head < 0 || llr_head >= e->d.n_io) return fail(NRX_ERR_INVALID, "nrx_mac_per_pixel: bad argument");
+    *macs = e->mac_fixed[llr_head] + e->mac_per_it * e->num_it;
+    return NRX_OK;
+}
+
+int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, const float* active_tx,
+                const int32_t* io_index, const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr,
+                float* llr_grid, float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes) {
+    if (!e || !y || !active_tx || !workspace) return fail(NRX_ERR_INVALID, "nrx_forward: null argument");
+    if (batch < 1) return fail(NRX_ERR_INVALID, "batch must be >= 1");
+    const nrx_model_desc& d = e->d;
+    if (llr_head < 0 || llr_head >= d.n_io) return fail(NRX_ERR_INVALID, "llr_head out of range");
+    if (out_bits < 1 || out_bits > 16) return fail(NRX_ERR_INVALID, "out_bits out of range");
+    const Workspace w = layout(e, batch);
+    if (workspace_bytes < w.total)
+        return fail(NRX_ERR_WORKSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, w.total);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(NRX_ERR_INVALID, "workspace must be 256-byte aligned");
+    NRX_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* partial = reinterpret_cast<float*>(ws + w.partial);
+    __half* z0 = reinterpret_cast<__half*>(ws + w.z0);
+    __half* h1 = reinterpret_cast<__half*>(ws + w.h1);
+    __half* h2 = reinterpret_cast<__half*>(ws + w.h2);
+    __half* abuf = reinterpret_cast<__half*>(ws + w.abuf);
+    __half* sbuf = reinterpret_cast<__half*>(ws + w.sbuf);
+
+    const int F = d.num_subcarriers, U = d.max_num_tx, N = d.num_rx_ant;
+    const int per_slot = F * kT;
+    nrx_power_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(static_cast<const float2*>(y), partial, N * per_slot);
+
+    const int bp_max = pass_slots(e, batch);
+    for (int b0 = 0; b0 < batch; b0 += bp_max) {
+        const int bp = batch - b0 < bp_max ? batch - b0 : bp_max;
+        const int BU = bp * U;
+        PrepParams pp{};
+        pp.y = static_cast<const float2*>(y);
+        pp.partial = partial;
+        pp.nn_index = e->nn_index;
+        pp.focc = e->focc;
+        pp.pos_enc = e->pos_enc;
+        pp.z0 = z0;
+        pp.h_ls = h_hat_ls;
+        pp.F = F; pp.U = U; pp.N = N; pp.n_pilot_slots = e->n_pilot_slots; pp.b0 = b0; pp.bp = bp;
+        nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
+
+        SepParams sp{};
+        sp.F = F; sp.U = U; sp.d_s = d.d_s;
+        sp.tiles_per_bu = (F + kTileF - 1) / kTileF;
+        sp.num_tiles = sp.tiles_per_bu * BU;
+        sp.pos_enc = e->pos_enc;
+        // ---- StateInit (:107-132), stack per user = one-hot mcs_ue_mask (:562-569) -------------
+        sp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
+        sp.default_stack = llr_head;
+        sp.src0 = z0; sp.src1 = nullptr; sp.C0 = 32; sp.C1 = 0; sp.out = h1;
+        sp.wblob = e->init_layers[0].blob; sp.blob_bytes = e->init_layers[0].blob_bytes;
+        launch_sep<32, 128, kHidden>(e, st, sp);
+        sp.src0 = h1; sp.C0 = 128; sp.out = h2;
+        sp.wblob = e->init_layers[1].blob; sp.blob_bytes = e->init_layers[1].blob_bytes;
+        launch_sep<128, 128, kHidden>(e, st, sp);
+        sp.src0 = h2; sp.out = sbuf;
+        sp.wblob = e->init_layers[2].blob; sp.blob_bytes = e->init_layers[2].blob_bytes;
+        launch_sep<128, 64, kInitOut>(e, st, sp);
+        // ---- CGNN iterations (:576-593) --------------------------------------------------------
+        sp.stack_index = nullptr;
+        sp.default_stack = 0;
+        for (int it = 0; it < e->num_it; ++it) {
+            AggParams ap{};
+            ap.sbuf = sbuf; ap.abuf = abuf; ap.wblob = e->agg_blobs[it];
+            ap.active_tx = active_tx + size_t(b0) * U;
+            ap.U = U; ap.rows_per_bu = per_slot;
+            ap.tiles_per_b = (per_slot + 127) / 128;
+            ap.num_tiles = ap.tiles_per_b * bp;
+            const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
+            const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
+            switch (U) {
+                case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
+                case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
+                case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
+                default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+            }
+            const auto& L = e->upd_layers[it];
+            sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
+            sp.wblob = L[0].blob; sp.blob_bytes = L[0].blob_bytes;
+            launch_sep<128, 128, kHidden>(e, st, sp);
+            sp.src0 = h1; sp.src1 = nullptr; sp.C0 = 128; sp.C1 = 0; sp.out = h2;
+            sp.wblob = L[1].blob; sp.blob_bytes = L[1].blob_bytes;
+            launch_sep<128, 128, kHidden>(e, st, sp);
+            sp.src0 = h2; sp.out = sbuf;
+            sp.wblob = L[2].blob; sp.blob_bytes = L[2].blob_bytes;
+            launch_sep<128, 64, kUpdateOut>(e, st, sp);
+        }
+        // ---- read-outs + resource-grid demapping (:582-593, :843-858) --------------------------
+        ReadoutParams rp{};
+        rp.sbuf = sbuf;
+        rp.wblob = e->readout_blob;
+        rp.head_index = head_index ? head_index + size_t(b0) * U : nullptr;
+        rp.data_index = e->data_index;
+        const size_t bu0 = size_t(b0) * U;
+        rp.llr = llr ? llr + bu0 * d.num_data_res * out_bits : nullptr;
+        rp.llr_grid = llr_grid ? llr_grid + bu0 * per_slot * out_bits : nullptr;
+        rp.h_ref = h_hat_refined ? h_hat_refined + bu0 * per_slot * 2 * N : nullptr;
+        rp.F = F; rp.U = U; rp.N2 = 2 * N; rp.out_bits = out_bits; rp.n_data = d.num_data_res;
+        rp.rows_per_bu = per_slot;
+        rp.tiles_per_bu = (per_slot + 127) / 128;
+        rp.num_tiles = rp.tiles_per_bu * BU;
+        rp.default_head = llr_head;
+        const int grid = rp.num_tiles < e->num_sms ? rp.num_tiles : e->num_sms;
+        nrx_readout_kernel<<<grid, kThreads, kRoSmem, st>>>(rp);
+    }
+    NRX_CUDA(cudaGetLastError());
+    return NRX_OK;
+}
+
+int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* active_tx, const int32_t* io_index,
+                     const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
+                     float* h_hat_refined, float* h_hat_ls) {
+    if (!e || !y || !active_tx) return fail(NRX_ERR_INVALID, "nrx_forward_host: null argument");
+    if (batch < 1) return fail(NRX_ERR_INVALID, "batch must be >= 1");
+    if (out_bits < 1 || out_bits > 16) return fail(NRX_ERR_INVALID, "out_bits out of range");
+    const nrx_model_desc& d = e->d;
+    NRX_CUDA(cudaSetDevice(e->device));
+    if (!e->stream) NRX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
+    const size_t BU = size_t(batch) * U;
+    // device / pinned arena layout (256-byte aligned pieces)
+    size_t off = 0;
+    auto piece = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_y = piece(size_t(batch) * d.num_rx_ant * per_slot * 8);
+    const size_t o_act = piece(BU * 4);
+    const size_t o_io = piece(BU * 4);
+    const size_t o_head = piece(BU * 4);
+    const size_t in_bytes = off;
+    const size_t o_llr = piece(llr ? BU * d.num_data_res * out_bits * 4 : 0);
+    const size_t o_grid = piece(llr_grid ? BU * per_slot * out_bits * 4 : 0);
+    const size_t o_href = piece(h_hat_refined ? BU * per_slot * N2 * 4 : 0);
+    const size_t o_hls = piece(h_hat_ls ? BU * per_slot * N2 * 4 : 0);
+    const size_t total = off;
+    if (total > e->d_io_bytes) {
+        cudaFree(e->d_io);
+        e->d_io = nullptr;
+        e->d_io_bytes = 0;
+        if (e->h_pin) cudaFreeHost(e->h_pin);
+        e->h_pin = nullptr;
+        NRX_CUDA(cudaMalloc(&e->d_io, total));
+        NRX_CUDA(cudaMallocHost(&e->h_pin, total));
+        e->d_io_bytes = e->h_pin_bytes = total;
+    }
+    const Workspace w = layout(e, batch);
+    if (w.total > e->d_ws_bytes) {
+        cudaFree(e->d_ws);
+        e->d_ws = nullptr;
+        e->d_ws_bytes = 0;
+        NRX_CUDA(cudaMalloc(&e->d_ws, w.total));
+        e->d_ws_bytes = w.total;
+    }
+    uint8_t* hp = static_cast<uint8_t*>(e->h_pin);
+    uint8_t* dp = static_cast<uint8_t*>(e->d_io);
+    memcpy(hp + o_y, y, size_t(batch) * d.num_rx_ant * per_slot * 8);
+    memcpy(hp + o_act, active_tx, BU * 4);
+    if (io_index) memcpy(hp + o_io, io_index, BU * 4);
+    if (head_index) memcpy(hp + o_head, head_index, BU * 4);
+    NRX_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = nrx_forward(e, e->stream, batch, dp + o_y, reinterpret_cast<const float*>(dp + o_act),
+                               io_index ? reinterpret_cast<const int32_t*>(dp + o_io) : nullptr,
+                               head_index ? reinterpret_cast<const int32_t*>(dp + o_head) : nullptr, llr_head, out_bits,
+                               llr ? reinterpret_cast<float*>(dp + o_llr) : nullptr,
+                               llr_grid ? reinterpret_cast<float*>(dp + o_grid) : nullptr,
+                               h_hat_refined ? reinterpret_cast<float*>(dp + o_href) : nullptr,
+                               h_hat_ls ? reinterpret_cast<float*>(dp + o_hls) : nullptr, e->d_ws, e->d_ws_bytes);
+    if (rc) return rc;
+    if (total > in_bytes)
+        NRX_CUDA(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, e->stream));
+    NRX_CUDA(cudaStreamSynchronize(e->stream));
+    if (llr) memcpy(llr, hp + o_llr, BU * d.num_data_res * out_bits * 4);
+    if (llr_grid) memcpy(llr_grid, hp + o_grid, BU * per_slot * out_bits * 4);
+    if (h_hat_refined) memcpy(h_hat_refined, hp + o_href, BU * per_slot * N2 * 4);
+    if (h_hat_ls) memcpy(h_hat_ls, hp + o_hls, BU * per_slot * N2 * 4);
+    return NRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,749 @@
+// nrx_kernels.cuh — sm_100a kernels of the neural-receiver hot path (CGNN forward,
+// reference utils/neural_rx.py:544-595 and its pre/post-processing :813-881, :1462-1514).
+//
+// Data layout in HBM (all activations channels-last fp16, one row per user resource element,
+// row index  p = ((b*U + u)*F + f)*14 + t ):
+//   z0    [P][32]   StateInit input  [y_re(N) y_im(N) pe_t pe_f h_re(N) h_im(N) 0..]   (normalised)
+//   H1/H2 [P][128]  hidden activations of a sep-conv stack (ping-pong)
+//   Abuf  [P][64]   aggregated messages a (56 valid, rest 0)
+//   Sbuf  [P][64]   state s (56 valid) | pe_t pe_f | 0 x 6   — the pe channels ride along so that
+//                   [Abuf | Sbuf] is the 128-wide UpdateState input [a, s, pe] (weights permuted)
+// GEMM operands are fp16 K-major SWIZZLE_128B slabs (sm100_prims.cuh), accumulators fp32 in TMEM.
+//
+// Tiling: one tile = 9 subcarriers x 14 symbols = 126 rows of one (slot, user) -> one M=128 UMMA
+// tile; F = 1584 = 9 * 176 so the evaluation grid has no ragged tile.  Depthwise 3x3 needs a
+// +-1 subcarrier halo (11 x 14 rows staged in shared memory by one 1-D bulk copy); the symbol
+// axis is entirely inside the tile.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sm100_prims.cuh"
+
+namespace nrx {
+
+constexpr int kT = 14;            // OFDM symbols per slot (symbol_allocation = [0, 14])
+constexpr int kTileF = 9;         // subcarriers per tile
+constexpr int kTileRows = kTileF * kT;          // 126
+constexpr int kHaloRows = (kTileF + 2) * kT;    // 154
+constexpr int kThreads = 256;
+constexpr int kPowerParts = 16;   // partial sums per slot for the input-power reduction
+
+enum SepMode : int { kHidden = 0, kInitOut = 1, kUpdateOut = 2 };
+
+__device__ __forceinline__ uint4 ld_shared_v4(const void* p) {
+    return *reinterpret_cast<const uint4*>(p);
+}
+__device__ __forceinline__ void st_shared_v4(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ __half2 u2h(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t h2u(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// =============================================================================================
+// 1. input power  (CGNN.forward normalisation, utils/neural_rx.py:551-553): partial sums of y^2
+// =============================================================================================
+// grid (kPowerParts, B), block 256.  y: [B][N*T*F] complex64 viewed as float2.
+__global__ void __launch_bounds__(256) nrx_power_kernel(const float2* __restrict__ y, float* __restrict__ partial,
+                                                        int n_complex) {
+    const int b = blockIdx.y, part = blockIdx.x;
+    const int per = (n_complex + kPowerParts - 1) / kPowerParts;
+    const int lo = part * per, hi = min(lo + per, n_complex);
+    const float2* yb = y + size_t(b) * n_complex;
+    float acc = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += 256) {
+        const float2 v = __ldg(yb + i);
+        acc = fmaf(v.x, v.x, acc);
+        acc = fmaf(v.y, v.y, acc);
+    }
+    __shared__ float red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {          // fixed-order tree: deterministic
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[b * kPowerParts + part] = red[0];
+}
+
+__device__ __forceinline__ float slot_gain(const float* __restrict__ partial, int b, int n_real) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPowerParts; ++i) s += partial[b * kPowerParts + i];
+    const float g = rsqrtf(s / float(n_real));
+    return isfinite(g) ? g : 0.f;                // divide_no_nan of the TF original
+}
+
+// =============================================================================================
+// 2. pre-processing: LS + FOCC + nearest-pilot broadcast, normalisation, positional encoding
+//    (NeuralPUSCHReceiver.estimate_channel utils/neural_rx.py:1462-1514, copy_pytorch.py:899-911;
+//     CGNNOFDM.forward :832-839; StateInit concat :112-123)
+// =============================================================================================
+struct FoccEntry {     // LS estimate of pilot slot k of user u = sum_m y[src[m]] * w[m]
+    int32_t src[2];    // flat RE index t*F + f of the contributing pilot REs
+    float2 w[2];       // 0.5 / pilot  (0 for a missing member)
+};
+
+struct PrepParams {
+    const float2* y;          // [B][N][T][F]
+    const float* partial;     // [B][kPowerParts]
+    const int32_t* nn_index;  // [U][T*F]
+    const FoccEntry* focc;    // [U][n_pilot_slots]
+    const float* pos_enc;     // [U][F][T][2]
+    __half* z0;               // [Bp*U*F*T][32]
+    float* h_ls;              // [B][U][F][T][2N] or null
+    int F, U, N, n_pilot_slots, b0, bp;
+};
+
+__global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
+    const int per_slot = p.F * kT;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= p.bp * per_slot) return;
+    const int bl = idx / per_slot, rem = idx - bl * per_slot;
+    const int f = rem / kT, t = rem - f * kT;
+    const int b = p.b0 + bl;
+    const int N = p.N;
+    const float g = slot_gain(p.partial, b, 2 * N * per_slot);
+    const float2* yb = p.y + size_t(b) * N * per_slot;
+    const int re = t * p.F + f;
+
+    float yre[8], yim[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+        if (a < N) {
+            const float2 v = __ldg(yb + size_t(a) * per_slot + re);
+            yre[a] = v.x;
+            yim[a] = v.y;
+        }
+    for (int u = 0; u < p.U; ++u) {
+        const int k = __ldg(p.nn_index + size_t(u) * per_slot + re);
+        const FoccEntry e = p.focc[size_t(u) * p.n_pilot_slots + k];
+        float hre[8], him[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+            if (a < N) {
+                const float2 y0 = __ldg(yb + size_t(a) * per_slot + e.src[0]);
+                const float2 y1 = __ldg(yb + size_t(a) * per_slot + e.src[1]);
+                hre[a] = y0.x * e.w[0].x - y0.y * e.w[0].y + (y1.x * e.w[1].x - y1.y * e.w[1].y);
+                him[a] = y0.x * e.w[0].y + y0.y * e.w[0].x + (y1.x * e.w[1].y + y1.y * e.w[1].x);
+            }
+        const float2 pe = *reinterpret_cast<const float2*>(p.pos_enc + ((size_t(u) * p.F + f) * kT + t) * 2);
+        __align__(16) __half row[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) row[c] = __float2half(0.f);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+            if (a < N) {
+                row[a] = __float2half(yre[a] * g);
+                row[N + a] = __float2half(yim[a] * g);
+                row[2 * N + 2 + a] = __float2half(hre[a] * g);
+                row[3 * N + 2 + a] = __float2half(him[a] * g);
+            }
+        row[2 * N] = __float2half(pe.x);
+        row[2 * N + 1] = __float2half(pe.y);
+        const size_t prow = (size_t(bl) * p.U + u) * per_slot + rem;
+        uint4* dst = reinterpret_cast<uint4*>(p.z0 + prow * 32);
+        const uint4* srcv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = srcv[c];
+        if (p.h_ls) {
+            float* ho = p.h_ls + ((size_t(b) * p.U + u) * per_slot + rem) * (2 * N);
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (a < N) {
+                    ho[a] = hre[a];
+                    ho[N + a] = him[a];
+                }
+        }
+    }
+}
+
+// =============================================================================================
+// 3. separable-conv layer: depthwise 3x3 (CUDA cores, HFMA2) -> swizzled A operand in smem ->
+//    pointwise GEMM on tcgen05 (fp32 accumulators in TMEM) -> bias / ReLU / residual epilogue
+//    (Keras SeparableConv2D of StateInit utils/neural_rx.py:61-132 and UpdateState :210-270)
+// =============================================================================================
+struct SepParams {
+    const __half* src0;        // [P][C0]
+    const __half* src1;        // [P][C1] or null        (C0 + C1 == KPAD)
+    const uint8_t* wblob;      // per stack: [pw image | dw taps [9][KPAD] fp16 | bias [NPAD] fp32]
+    const int32_t* stack_index;// [BU] (already offset to the pass) or null
+    __half* out;               // kHidden: [P][NPAD]; kInitOut / kUpdateOut: Sbuf [P][64]
+    const float* pos_enc;      // [U][F][T][2]   (kInitOut)
+    int C0, C1;
+    int F, U, d_s;
+    int tiles_per_bu, num_tiles;
+    int default_stack;
+    uint32_t blob_bytes;
+};
+
+template <int KPAD, int NPAD>
+struct SepSmem {
+    static constexpr int KS = (KPAD + 63) / 64;
+    static constexpr int kA = 32768;                         // A operand, later the output staging
+    static constexpr int kWpw = KS * NPAD * 128;
+    static constexpr int kDw = 9 * KPAD * 2;
+    static constexpr int kBias = NPAD * 4;
+    static constexpr int kBlob = kWpw + kDw + kBias;
+    static constexpr int kIn = kHaloRows * KPAD * 2;
+    static constexpr int offA = 0;
+    static constexpr int offW = kA;
+    static constexpr int offIn = ((offW + kBlob + 127) / 128) * 128;
+    static constexpr int kTotal = offIn + kIn + 1024;        // + alignment slack
+};
+
+template <int KPAD, int NPAD, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) nrx_sepconv_kernel(SepParams p) {
+    using L = SepSmem<KPAD, NPAD>;
+    constexpr int KS = L::KS;
+    constexpr int NCV = KPAD / 8;                  // 16-byte channel vectors per row
+    constexpr int NSEG = (KPAD >= 128) ? 1 : 3;    // subcarrier segments per thread column
+    constexpr int SEGF = kTileF / NSEG;
+    constexpr int NTASK = NSEG * kT * NCV;
+    static_assert(NTASK <= kThreads, "depthwise task mapping");
+    static_assert(MODE == kHidden || NPAD == 64, "state output is 64 wide");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem + L::offA;
+    uint8_t* sW = smem + L::offW;
+    const __half* sDw = reinterpret_cast<const __half*>(sW + L::kWpw);
+    const float* sBias = reinterpret_cast<const float*>(sW + L::kWpw + L::kDw);
+    uint8_t* sIn = smem + L::offIn;
+    __shared__ uint64_t bar_in, bar_w, bar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (tid == 0) {
+        mbar_init(&bar_in, 1);
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    uint32_t ph_in = 0, ph_w = 0, ph_mma = 0;
+    int loaded_stack = -1;
+
+    const int rowB0 = p.C0 * 2, rowB1 = p.C1 * 2;
+    uint8_t* sIn0 = sIn;
+    uint8_t* sIn1 = sIn + kHaloRows * rowB0;
+
+    // issue the halo-tile load of `tile` (thread 0) and zero the out-of-grid halo rows (all threads)
+    auto stage_input = [&](int tile) {
+        const int bu = tile / p.tiles_per_bu, ft = tile - bu * p.tiles_per_bu;
+        const int f0 = ft * kTileF;
+        const int flo = max(f0 - 1, 0), fhi = min(f0 + kTileF + 1, p.F);     // valid [flo, fhi)
+        const int fi_lo = flo - (f0 - 1), fi_hi = fhi - (f0 - 1);            // halo-row indices
+        if (tid == 0) {
+            const uint32_t nrow = uint32_t(fhi - flo) * kT;
+            mbar_arrive_expect_tx(&bar_in, nrow * uint32_t(rowB0 + rowB1));
+            const size_t grow = (size_t(bu) * p.F + flo) * kT;
+            bulk_g2s(sIn0 + fi_lo * kT * rowB0, reinterpret_cast<const uint8_t*>(p.src0) + grow * rowB0,
+                     nrow * rowB0, &bar_in);
+            if (rowB1)
+                bulk_g2s(sIn1 + fi_lo * kT * rowB1, reinterpret_cast<const uint8_t*>(p.src1) + grow * rowB1,
+                         nrow * rowB1, &bar_in);
+        }
+        // rows [0, fi_lo) and [fi_hi, 11) are outside the grid: zero ('same' padding)
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const int v0 = rowB0 / 16, v1 = rowB1 / 16;
+        for (int fi = 0; fi < kTileF + 2; ++fi) {
+            if (fi >= fi_lo && fi < fi_hi) continue;
+            for (int i = tid; i < kT * (v0 + v1); i += kThreads) {
+                if (i < kT * v0) st_shared_v4(sIn0 + fi * kT * rowB0 + i * 16, z);
+                else st_shared_v4(sIn1 + fi * kT * rowB1 + (i - kT * v0) * 16, z);
+            }
+        }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles) stage_input(tile);
+
+    while (tile < p.num_tiles) {
+        const int bu = tile / p.tiles_per_bu, ft = tile - bu * p.tiles_per_bu;
+        const int f0 = ft * kTileF;
+        const int valid_rows = min(kTileF, p.F - f0) * kT;
+        const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
+        if (stack != loaded_stack) {                 // block-uniform; first tile or Var-IO switch
+            __syncthreads();                         // nobody still reads the old taps / bias
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar_w, p.blob_bytes);
+                bulk_g2s(sW, p.wblob + size_t(stack) * p.blob_bytes, p.blob_bytes, &bar_w);
+            }
+            mbar_wait(&bar_w, ph_w);
+            ph_w ^= 1;
+            loaded_stack = stack;
+        }
+        mbar_wait(&bar_in, ph_in);
+        ph_in ^= 1;
+        __syncthreads();                             // zero-filled halo rows of this tile visible
+
+        // ---------------- depthwise 3x3: thread = (segment, symbol t, channel vector cv) ------
+        if (tid < NTASK) {
+            const int cv = tid % NCV;
+            const int t = (tid / NCV) % kT;
+            const int seg = tid / (NCV * kT);
+            const uint8_t* base;
+            int rowB;
+            if (cv * 8 < p.C0) { base = sIn0 + cv * 16; rowB = rowB0; }
+            else { base = sIn1 + (cv * 8 - p.C0) * 2; rowB = rowB1; }
+            uint4 kk[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) kk[i] = ld_shared_v4(reinterpret_cast<const uint8_t*>(sDw) + (i * KPAD + cv * 8) * 2);
+            const bool has_l = t > 0, has_r = t < kT - 1;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            uint4 win[3][3];
+            auto load_row = [&](int fi, uint4 (&r)[3]) {
+                const uint8_t* q = base + (fi * kT + t) * rowB;
+                r[0] = has_l ? ld_shared_v4(q - rowB) : z;
+                r[1] = ld_shared_v4(q);
+                r[2] = has_r ? ld_shared_v4(q + rowB) : z;
+            };
+            const int fs = seg * SEGF;               // first output subcarrier (tile-local)
+            load_row(fs, win[0]);                    // halo index fi = f_local + 1 -> f_local - 1 is fi = f_local
+            load_row(fs + 1, win[1]);
+#pragma unroll
+            for (int s = 0; s < SEGF; ++s) {
+                const int fl = fs + s;
+                load_row(fl + 2, win[(s + 2) % 3]);
+                __half2 acc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = __float2half2_rn(0.f);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const uint4(&r)[3] = win[(s + i) % 3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint4 x = r[j], w = kk[i * 3 + j];
+                        acc[0] = __hfma2(u2h(x.x), u2h(w.x), acc[0]);
+                        acc[1] = __hfma2(u2h(x.y), u2h(w.y), acc[1]);
+                        acc[2] = __hfma2(u2h(x.z), u2h(w.z), acc[2]);
+                        acc[3] = __hfma2(u2h(x.w), u2h(w.w), acc[3]);
+                    }
+                }
+                const int r = fl * kT + t;
+                st_shared_v4(sA + (cv >> 3) * 16384 + r * 128 + (((cv & 7) ^ (r & 7)) << 4),
+                             make_uint4(h2u(acc[0]), h2u(acc[1]), h2u(acc[2]), h2u(acc[3])));
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();                             // A operand complete, sIn free
+
+        if (tid == 0) {
+            tc_fence_after_sync();
+            umma_gemm_k(tbase, smem_u32(sA), 16384, smem_u32(sW), NPAD * 128, KPAD, umma_idesc_f16(128, NPAD), false);
+            umma_commit(&bar_mma);
+        }
+        const int next = tile + gridDim.x;
+        if (next < p.num_tiles) stage_input(next);   // overlaps the GEMM and the epilogue
+
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+
+        // ---------------- epilogue: TMEM -> registers -> staging (A buffer, now free) ----------
+        const int q = warp & 3, hcol = warp >> 2;
+        const int r = q * 32 + lane;
+        if constexpr (MODE == kHidden) {
+            constexpr int COLS = NPAD / 2;           // columns per warp
+#pragma unroll
+            for (int c0 = 0; c0 < COLS; c0 += 32) {
+                float v[32];
+                const int col = hcol * COLS + c0;
+                tmem_ld32(tmem_addr(tbase, q * 32, col), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a = fmaxf(v[j + 2 * e] + sBias[col + j + 2 * e], 0.f);
+                        const float b = fmaxf(v[j + 2 * e + 1] + sBias[col + j + 2 * e + 1], 0.f);
+                        pk[e] = pack_half2(a, b);
+                    }
+                    const int cc = (col + j) >> 3;
+                    st_shared_v4(sA + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4),
+                                 make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                }
+            }
+        } else {
+            // fp32 staging [128][64]: 16 chunks of 4 floats per row, chunk index XOR (row & 7)
+            float v[32];
+            const int col = hcol * 32;
+            tmem_ld32(tmem_addr(tbase, q * 32, col), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int c4 = (col + j) >> 2;
+                float4 o;
+                o.x = v[j] + sBias[col + j];
+                o.y = v[j + 1] + sBias[col + j + 1];
+                o.z = v[j + 2] + sBias[col + j + 2];
+                o.w = v[j + 3] + sBias[col + j + 3];
+                *reinterpret_cast<float4*>(sA + r * 256 + ((c4 ^ (r & 7)) << 4)) = o;
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();                             // staging complete; TMEM drained
+
+        // ---------------- coalesced copy-out ---------------------------------------------------
+        const size_t row0 = (size_t(bu) * p.F + f0) * kT;
+        if constexpr (MODE == kHidden) {
+            constexpr int CPR = NPAD / 8;            // 16-byte chunks per row
+            for (int i = tid; i < valid_rows * CPR; i += kThreads) {
+                const int rr = i / CPR, cc = i - rr * CPR;
+                const uint4 val = ld_shared_v4(sA + (cc >> 3) * 16384 + rr * 128 + (((cc & 7) ^ (rr & 7)) << 4));
+                *reinterpret_cast<uint4*>(p.out + (row0 + rr) * NPAD + cc * 8) = val;
+            }
+        } else {
+            const int u = bu % p.U;
+            for (int i = tid; i < valid_rows * 16; i += kThreads) {
+                const int rr = i >> 4, c4 = i & 15;
+                const float4 o = *reinterpret_cast<const float4*>(sA + rr * 256 + ((c4 ^ (rr & 7)) << 4));
+                __half* dst = p.out + (row0 + rr) * 64 + c4 * 4;
+                float a0 = o.x, a1 = o.y, a2 = o.z, a3 = o.w;
+                if constexpr (MODE == kUpdateOut) {  // residual: s <- s + update  (:266)
+                    const uint2 old = *reinterpret_cast<const uint2*>(dst);
+                    const float2 o01 = __half22float2(u2h(old.x)), o23 = __half22float2(u2h(old.y));
+                    a0 += o01.x; a1 += o01.y; a2 += o23.x; a3 += o23.y;
+                } else {                             // state init: append the positional encoding
+                    const int pe_chunk = p.d_s >> 2;
+                    if (c4 == pe_chunk) {
+                        const int fl = rr / kT, tt = rr - fl * kT;
+                        const float2 pe = *reinterpret_cast<const float2*>(
+                            p.pos_enc + ((size_t(u) * p.F + f0 + fl) * kT + tt) * 2);
+                        a0 = pe.x; a1 = pe.y; a2 = 0.f; a3 = 0.f;
+                    } else if (c4 > pe_chunk) {
+                        a0 = a1 = a2 = a3 = 0.f;
+                    }
+                }
+                uint2 pk;
+                pk.x = pack_half2(a0, a1);
+                pk.y = pack_half2(a2, a3);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            }
+        }
+        __syncthreads();                             // staging free before the next depthwise pass
+        tile = next;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 128);
+}
+
+// =============================================================================================
+// 4. AggregateUserStates (utils/neural_rx.py:135-207): per-RE MLP d_s -> units_agg -> d_s on every
+//    user's state, masked sum over the *other* users, 1/(n_active-1) scaling.  One CTA holds the
+//    same 128 resource elements of all U users, so the cross-user reduction is CTA-local.
+// =============================================================================================
+struct AggParams {
+    const __half* sbuf;        // [Bp*U*F*T][64]
+    __half* abuf;              // [Bp*U*F*T][64]
+    const uint8_t* wblob;      // [W1 image 64x64 | W2 image 64x64 | b1[64] | b2[64]]
+    const float* active_tx;    // [Bp][U] (already offset to the pass)
+    int U, rows_per_bu, tiles_per_b, num_tiles;
+};
+
+constexpr int kAggBlob = 8192 + 8192 + 256 + 256;
+constexpr int kAggMaxU = 4;
+
+__host__ __device__ constexpr int agg_smem_bytes(int U) { return U * 32768 + ((kAggBlob + 127) / 128) * 128 + 1024; }
+
+template <int U>
+__global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(AggParams p) {
+    constexpr uint32_t TM_COLS = (U <= 1) ? 64 : (U == 2) ? 128 : 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                      // [U][128 rows][128 B]  state tiles, later the output staging
+    uint8_t* sH = smem + U * 16384;          // [U][128][128 B]       hidden activations
+    uint8_t* sW = smem + U * 32768;
+    const float* sB1 = reinterpret_cast<const float*>(sW + 16384);
+    const float* sB2 = sB1 + 64;
+    __shared__ uint64_t bar_w, bar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&bar_w, kAggBlob);
+        bulk_g2s(sW, p.wblob, kAggBlob, &bar_w);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    mbar_wait(&bar_w, 0);
+    uint32_t ph_mma = 0;
+    const int q = warp & 3, hcol = warp >> 2;
+    const int r = q * 32 + lane;
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
+        const int r0 = rt * 128;
+        const int valid_rows = min(128, p.rows_per_bu - r0);
+        // ---- stage the state rows of all users into swizzled A tiles ------------------------
+        for (int i = tid; i < U * 128 * 8; i += kThreads) {
+            const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (rr < valid_rows)
+                val = *reinterpret_cast<const uint4*>(p.sbuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8);
+            st_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4), val);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                umma_gemm_k(tbase + u * 64, smem_u32(sA + u * 16384), 16384, smem_u32(sW), 8192, 64,
+                            umma_idesc_f16(128, 64), false);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        // ---- hidden layer epilogue: ReLU(acc + b1) -> fp16 -> sH ------------------------------
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float v[32];
+            const int col = hcol * 32;
+            tmem_ld32(tmem_addr(tbase + u * 64, q * 32, col), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    pk[e] = pack_half2(fmaxf(v[j + 2 * e] + sB1[col + j + 2 * e], 0.f),
+                                       fmaxf(v[j + 2 * e + 1] + sB1[col + j + 2 * e + 1], 0.f));
+                const int cc = (col + j) >> 3;
+                st_shared_v4(sH + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                umma_gemm_k(tbase + u * 64, smem_u32(sH + u * 16384), 16384, smem_u32(sW + 8192), 8192, 64,
+                            umma_idesc_f16(128, 64), false);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        // ---- output epilogue: masked sum over the other users (:192-204) -> staging in sA ------
+        {
+            float m[U], n_act = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                m[u] = p.active_tx[b * U + u];
+                n_act += m[u];
+            }
+            const float pm = fmaxf(n_act - 1.f, 0.f);
+            const float scale = (pm == 0.f) ? 1.f : 1.f / pm;
+            const int col = hcol * 32;
+            float sp[U][32];
+#pragma unroll
+            for (int u = 0; u < U; ++u) tmem_ld32(tmem_addr(tbase + u * 64, q * 32, col), sp[u]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float tot = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    sp[u][j] = (sp[u][j] + sB2[col + j]) * m[u];
+                    tot += sp[u][j];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) sp[u][j] = (tot - sp[u][j]) * scale;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const int cc = (col + j) >> 3;
+                    st_shared_v4(sA + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4),
+                                 make_uint4(pack_half2(sp[u][j], sp[u][j + 1]), pack_half2(sp[u][j + 2], sp[u][j + 3]),
+                                            pack_half2(sp[u][j + 4], sp[u][j + 5]), pack_half2(sp[u][j + 6], sp[u][j + 7])));
+                }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        for (int i = tid; i < U * 128 * 8; i += kThreads) {
+            const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
+            if (rr < valid_rows)
+                *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
+                    ld_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        }
+        __syncthreads();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TM_COLS);
+}
+
+// =============================================================================================
+// 5. read-outs (ReadoutLLRs utils/neural_rx.py:309-355, ReadoutChEst :358-404) fused with the
+//    resource-grid demapping of CGNNOFDM.forward (:843-858; ordering utils/onnx_utils.py:486-514).
+//    Both heads share one GEMM chain: hidden [128 x 256] = s . [W_llr1 | W_h1], then
+//    [128 x 32] = hidden . blockdiag(W_llr2, W_h2).
+// =============================================================================================
+struct ReadoutParams {
+    const __half* sbuf;          // [Bp*U*F*T][64]
+    const uint8_t* wblob;        // per LLR head: [W1 image 256x64 | W2 image 32x256 | b1[256] | b2[32]]
+    const int32_t* head_index;   // [Bp*U] or null
+    const int32_t* data_index;   // [T*F]: ordinal among data REs or -1
+    float* llr;                  // [Bp][U][n_data*out_bits] or null
+    float* llr_grid;             // [Bp][U][F][T][out_bits]  or null
+    float* h_ref;                // [Bp][U][F][T][2N]        or null
+    int F, U, N2, out_bits, n_data;
+    int rows_per_bu, tiles_per_bu, num_tiles, default_head;
+};
+
+constexpr int kRoW1 = 256 * 128, kRoW2 = 4 * 32 * 128;
+constexpr int kRoBlob = kRoW1 + kRoW2 + 1024 + 128;
+constexpr int kRoSmem = 16384 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                   // [128][128 B]
+    uint8_t* sH = smem + 16384;           // 4 slabs [128][128 B]
+    uint8_t* sW = smem + 16384 + 65536;
+    const float* sB1 = reinterpret_cast<const float*>(sW + kRoW1 + kRoW2);
+    const float* sB2 = sB1 + 256;
+    __shared__ uint64_t bar_w, bar_mma;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    uint32_t ph_w = 0, ph_mma = 0;
+    int loaded_head = -1;
+    const int q = warp & 3, hcol = warp >> 2;
+    const int r = q * 32 + lane;
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
+        const int r0 = rt * 128;
+        const int valid_rows = min(128, p.rows_per_bu - r0);
+        const int head = p.head_index ? p.head_index[bu] : p.default_head;
+        if (head != loaded_head) {
+            __syncthreads();
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar_w, kRoBlob);
+                bulk_g2s(sW, p.wblob + size_t(head) * kRoBlob, kRoBlob, &bar_w);
+            }
+            mbar_wait(&bar_w, ph_w);
+            ph_w ^= 1;
+            loaded_head = head;
+        }
+        for (int i = tid; i < 128 * 8; i += kThreads) {
+            const int rr = i >> 3, cc = i & 7;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (rr < valid_rows)
+                val = *reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8);
+            st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), val);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            umma_gemm_k(tbase, smem_u32(sA), 16384, smem_u32(sW), 256 * 128, 64, umma_idesc_f16(128, 256), false);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            float v[32];
+            const int col = hcol * 128 + c0;
+            tmem_ld32(tmem_addr(tbase, q * 32, col), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    pk[e] = pack_half2(fmaxf(v[j + 2 * e] + sB1[col + j + 2 * e], 0.f),
+                                       fmaxf(v[j + 2 * e + 1] + sB1[col + j + 2 * e + 1], 0.f));
+                const int cc = (col + j) >> 3;
+                st_shared_v4(sH + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4),
+                             make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after_sync();
+            umma_gemm_k(tbase + 256, smem_u32(sH), 16384, smem_u32(sW + kRoW1), 32 * 128, 256,
+                        umma_idesc_f16(128, 32), false);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        if (warp < 4) {
+            float v[32];
+            tmem_ld32(tmem_addr(tbase + 256, q * 32, 0), v);
+            tmem_ld_wait();
+            if (r < valid_rows) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += sB2[j];
+                const int prow = r0 + r;                      // row inside the (slot, user) grid
+                const int f = prow / kT, t = prow - f * kT;
+                const size_t grow = size_t(bu) * p.rows_per_bu + prow;
+                if (p.llr_grid) {
+                    float* o = p.llr_grid + grow * p.out_bits;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < p.out_bits) o[j] = v[j];
+                }
+                if (p.llr) {
+                    const int d = p.data_index[t * p.F + f];
+                    if (d >= 0) {
+                        float* o = p.llr + (size_t(bu) * p.n_data + d) * p.out_bits;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < p.out_bits) o[j] = v[j];
+                    }
+                }
+                if (p.h_ref) {
+                    float* o = p.h_ref + grow * p.N2;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < p.N2) o[j] = v[16 + j];
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace nrx

@@ -1,0 +1,277 @@
+"""ctypes binding of ``libnrx_b200.so`` (C ABI in ``include/nrx_b200.h``).
+
+PyTorch only provides device buffers and the CUDA stream; every arithmetic step of the receiver
+runs inside the library's sm_100a kernels.  A missing library is a hard error (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from .config import NrxConfig
+from .pusch import PuschGrid
+from .weights import NrxWeights
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnrx_b200.so")
+
+NRX_MAX_IO = 4
+NRX_MAX_DMRS = 4
+
+#: every symbol declared in include/nrx_b200.h
+EXPORTED_SYMBOLS = (
+    "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass",
+    "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_launches_per_forward",
+    "nrx_mac_per_pixel", "nrx_last_error", "nrx_version",
+)
+
+
+class NrxError(RuntimeError):
+    """Non-zero status from the C ABI (message from ``nrx_last_error``)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libnrx_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ModelDesc(ctypes.Structure):
+    """``nrx_model_desc`` of include/nrx_b200.h."""
+
+    _fields_ = [
+        ("num_rx_ant", ctypes.c_int32), ("max_num_tx", ctypes.c_int32),
+        ("num_subcarriers", ctypes.c_int32), ("num_ofdm_symbols", ctypes.c_int32),
+        ("d_s", ctypes.c_int32), ("num_it", ctypes.c_int32),
+        ("units_init", ctypes.c_int32 * 2), ("units_agg", ctypes.c_int32),
+        ("units_state", ctypes.c_int32 * 2), ("units_readout", ctypes.c_int32),
+        ("n_io", ctypes.c_int32), ("io_bits", ctypes.c_int32 * NRX_MAX_IO),
+        ("num_dmrs_symbols", ctypes.c_int32), ("dmrs_symbols", ctypes.c_int32 * NRX_MAX_DMRS),
+        ("focc_block", ctypes.c_int32), ("num_data_res", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Load the shared object and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build the CUDA library first (python -m neural_rx_b200.build). "
+            "The receiver has no CPU fallback.")
+    lib = ctypes.CDLL(p)
+    c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+    f32p, i32p = ctypes.c_void_p, ctypes.c_void_p
+    lib.nrx_create.argtypes = [ctypes.POINTER(ModelDesc), ctypes.POINTER(ctypes.c_void_p),
+                               ctypes.POINTER(ctypes.c_int64), ctypes.c_int32, f32p, i32p, f32p, i32p,
+                               ctypes.c_int32, c_void_pp]
+    lib.nrx_destroy.argtypes = [ctypes.c_void_p]
+    lib.nrx_set_num_it.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_get_num_it.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
+    lib.nrx_set_slots_per_pass.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]
+    lib.nrx_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p,
+                                i32p, i32p, ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p,
+                                ctypes.c_void_p, ctypes.c_size_t]
+    lib.nrx_forward_host.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p, i32p, i32p,
+                                     ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p]
+    lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
+    lib.nrx_last_error.restype = ctypes.c_char_p
+    lib.nrx_version.restype = ctypes.c_char_p
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("nrx_last_error", "nrx_version"):
+            fn.restype = ctypes.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def make_desc(cfg: NrxConfig, grid: PuschGrid) -> ModelDesc:
+    """Fill ``nrx_model_desc`` from the receiver configuration (what CGNN.__init__ reads,
+    utils/neural_rx.py:407-530, 638-662) and the PUSCH grid."""
+    cfg.validate()
+    if len(cfg.num_units_init) != 2 or any(len(x) != 2 for x in cfg.num_units_state) \
+            or any(len(x) != 1 for x in cfg.num_units_agg) or len(cfg.num_units_readout) != 1:
+        raise NotImplementedError("the B200 engine implements 2 hidden sep-conv layers per stack and "
+                                  "1 hidden layer in the aggregation / read-out MLPs")
+    if len({tuple(x) for x in cfg.num_units_state}) != 1 or len({tuple(x) for x in cfg.num_units_agg}) != 1:
+        raise NotImplementedError("all iterations must share the same layer widths")
+    d = ModelDesc()
+    d.num_rx_ant = cfg.num_rx_antennas
+    d.max_num_tx = grid.num_tx
+    d.num_subcarriers = grid.num_subcarriers
+    d.num_ofdm_symbols = grid.num_ofdm_symbols
+    d.d_s = cfg.d_s
+    d.num_it = cfg.num_nrx_iter
+    d.units_init[0], d.units_init[1] = cfg.num_units_init
+    d.units_agg = cfg.num_units_agg[0][0]
+    d.units_state[0], d.units_state[1] = cfg.num_units_state[0]
+    d.units_readout = cfg.num_units_readout[0]
+    bits = cfg.readout_bits
+    d.n_io = len(bits)
+    for i, b in enumerate(bits):
+        d.io_bits[i] = b
+    d.num_dmrs_symbols = len(grid.dmrs_symbols)
+    for i, s in enumerate(grid.dmrs_symbols):
+        d.dmrs_symbols[i] = s
+    d.focc_block = grid.focc_block
+    d.num_data_res = grid.num_data_res
+    return d
+
+
+class NrxEngine:
+    """One engine = one (architecture, weight file, PUSCH grid) on one GPU."""
+
+    def __init__(self, cfg: NrxConfig, weights: NrxWeights, grid: PuschGrid, device: int = 0):
+        self._lib = load_library()
+        self.cfg, self.grid, self.device = cfg, grid, int(device)
+        self.desc = make_desc(cfg, grid)
+        arrays = [np.ascontiguousarray(a, dtype=np.float32) for a in weights.to_list()]
+        ptrs = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        sizes = (ctypes.c_int64 * len(arrays))(*[a.size for a in arrays])
+        pil = np.ascontiguousarray(grid.pilots.astype(np.complex64)).view(np.float32)
+        nn = np.ascontiguousarray(grid.nn_index, dtype=np.int32)
+        pe = np.ascontiguousarray(grid.pos_enc, dtype=np.float32)
+        di = np.ascontiguousarray(grid.data_index, dtype=np.int32)
+        handle = ctypes.c_void_p()
+        self._check(self._lib.nrx_create(ctypes.byref(self.desc), ptrs, sizes, len(arrays), pil.ctypes.data,
+                                         nn.ctypes.data, pe.ctypes.data, di.ctypes.data, self.device,
+                                         ctypes.byref(handle)))
+        self._h = handle
+        self._ws = None
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise NrxError(rc, self._lib.nrx_last_error().decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.nrx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_it(self) -> int:
+        v = ctypes.c_int32()
+        self._check(self._lib.nrx_get_num_it(self._h, ctypes.byref(v)))
+        return v.value
+
+    @num_it.setter
+    def num_it(self, val: int) -> None:
+        self._check(self._lib.nrx_set_num_it(self._h, int(val)))
+
+    def set_slots_per_pass(self, slots: int) -> None:
+        self._check(self._lib.nrx_set_slots_per_pass(self._h, int(slots)))
+        self._ws = None
+
+    def workspace_bytes(self, batch: int) -> int:
+        v = ctypes.c_size_t()
+        self._check(self._lib.nrx_workspace_bytes(self._h, int(batch), ctypes.byref(v)))
+        return v.value
+
+    def launches_per_forward(self, batch: int) -> int:
+        v = ctypes.c_int32()
+        self._check(self._lib.nrx_launches_per_forward(self._h, int(batch), ctypes.byref(v)))
+        return v.value
+
+    def mac_per_pixel(self, llr_head: int = 0) -> int:
+        v = ctypes.c_int64()
+        self._check(self._lib.nrx_mac_per_pixel(self._h, int(llr_head), ctypes.byref(v)))
+        return v.value
+
+    def flops_per_slot(self, llr_head: int = 0) -> float:
+        """Algorithmic FLOPs of one slot: 2 * U * F * T * MAC_per_pixel."""
+        g = self.grid
+        return 2.0 * g.num_tx * g.num_subcarriers * g.num_ofdm_symbols * self.mac_per_pixel(llr_head)
+
+    def _out_bits(self, llr_head: int, head_index, out_bits: Optional[int]) -> int:
+        if out_bits is not None:
+            return int(out_bits)
+        bits = self.cfg.readout_bits
+        return max(bits) if head_index is not None else bits[llr_head]
+
+    # ---- device call (torch tensors) ------------------------------------------------------------
+    def forward(self, y, active_tx, io_index=None, head_index=None, llr_head: int = 0,
+                out_bits: Optional[int] = None, want: Sequence[str] = ("llr", "h_hat_refined", "h_hat"),
+                out: Optional[Dict] = None, stream=None) -> Dict:
+        """``y`` complex64 CUDA tensor [B,1,N_rx,T,F]; ``active_tx`` float32 CUDA [B,U];
+        ``io_index`` / ``head_index`` int32 CUDA [B,U] or None.  Enqueues on the current stream
+        and returns CUDA tensors (keys of ``want`` among llr, llr_grid, h_hat_refined, h_hat)."""
+        import torch
+
+        g, N = self.grid, self.cfg.num_rx_antennas
+        B = int(y.shape[0])
+        if tuple(y.shape) != (B, 1, N, g.num_ofdm_symbols, g.num_subcarriers) or y.dtype != torch.complex64:
+            raise ValueError(f"y must be complex64 [B,1,{N},{g.num_ofdm_symbols},{g.num_subcarriers}], "
+                             f"got {tuple(y.shape)} {y.dtype}")
+        if not y.is_cuda or y.device.index != self.device:
+            raise ValueError("y must live on the engine's CUDA device")
+        U = g.num_tx
+        y = y.contiguous()
+        active_tx = active_tx.to(dtype=torch.float32).contiguous()
+        if tuple(active_tx.shape) != (B, U):
+            raise ValueError(f"active_tx must be [B,{U}]")
+        dev = y.device
+        bits = self._out_bits(llr_head, head_index, out_bits)
+        res = {} if out is None else out
+        per = g.num_subcarriers * g.num_ofdm_symbols
+        shapes = {"llr": (B, U, g.num_data_res * bits), "llr_grid": (B, U, g.num_subcarriers, g.num_ofdm_symbols, bits),
+                  "h_hat_refined": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N),
+                  "h_hat": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N)}
+        for k in want:
+            if k not in res:
+                res[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        ptr = lambda k: res[k].data_ptr() if k in want else None
+        iptr = lambda t: None if t is None else t.to(dtype=torch.int32).contiguous()
+        io_t, head_t = iptr(io_index), iptr(head_index)
+        st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        self._check(self._lib.nrx_forward(
+            self._h, ctypes.c_void_p(st), B, y.data_ptr(), active_tx.data_ptr(),
+            None if io_t is None else io_t.data_ptr(), None if head_t is None else head_t.data_ptr(),
+            int(llr_head), bits, ptr("llr"), ptr("llr_grid"), ptr("h_hat_refined"), ptr("h_hat"),
+            self._ws.data_ptr(), self._ws.numel()))
+        res["_keepalive"] = (y, active_tx, io_t, head_t)
+        del per
+        return res
+
+    # ---- host call (NumPy arrays, H2D + D2H inside) --------------------------------------------
+    def forward_host(self, y: np.ndarray, active_tx: np.ndarray, io_index=None, head_index=None,
+                     llr_head: int = 0, out_bits: Optional[int] = None,
+                     want: Sequence[str] = ("llr", "h_hat_refined", "h_hat")) -> Dict[str, np.ndarray]:
+        g, N = self.grid, self.cfg.num_rx_antennas
+        y = np.ascontiguousarray(y, dtype=np.complex64)
+        B, U = y.shape[0], g.num_tx
+        if y.shape != (B, 1, N, g.num_ofdm_symbols, g.num_subcarriers):
+            raise ValueError(f"y must be [B,1,{N},{g.num_ofdm_symbols},{g.num_subcarriers}], got {y.shape}")
+        act = np.ascontiguousarray(active_tx, dtype=np.float32)
+        if act.shape != (B, U):
+            raise ValueError(f"active_tx must be [B,{U}]")
+        bits = self._out_bits(llr_head, head_index, out_bits)
+        shapes = {"llr": (B, U, g.num_data_res * bits), "llr_grid": (B, U, g.num_subcarriers, g.num_ofdm_symbols, bits),
+                  "h_hat_refined": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N),
+                  "h_hat": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N)}
+        res = {k: np.empty(shapes[k], np.float32) for k in want}
+        io = None if io_index is None else np.ascontiguousarray(io_index, dtype=np.int32).reshape(B, U)
+        hd = None if head_index is None else np.ascontiguousarray(head_index, dtype=np.int32).reshape(B, U)
+        ptr = lambda k: res[k].ctypes.data if k in res else None
+        self._check(self._lib.nrx_forward_host(
+            self._h, B, y.ctypes.data, act.ctypes.data, None if io is None else io.ctypes.data,
+            None if hd is None else hd.ctypes.data, int(llr_head), bits, ptr("llr"), ptr("llr_grid"),
+            ptr("h_hat_refined"), ptr("h_hat")))
+        return res
