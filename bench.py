@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the neural-receiver full-slot hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One *step* = one pass of the hot path over one batch of ``batch_size_eval`` = 30 synthetic slots of
+BASELINE.json ``configs[1]`` (nrx_large, 132 PRB, 2 UEs, 4 rx antennas, 16-QAM) per GPU.  Prints ONE
+JSON line: ``value`` = whole-job slots/s with inputs resident in HBM, ``e2e`` = the same through
+the host-buffer C-ABI call (H2D + D2H inside the timed region), plus ``roofline`` (dominant
+kernel, CUDA events around every launch), ``cpu_baseline`` (the oracle port on the host cores),
+``latency_us`` (batch-1 p50 / p99 for nrx_rt and nrx_large) and ``clocks``.
+
+``--impl reference`` times the reference's own CPU path.  TensorFlow and Sionna are not
+installable here and the fork's torch port does not run, so that arm is the
+oracle restatement (``oracle/nrx_oracle.py``, PyTorch-CPU fp32, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from neural_rx_b200.config import get_config  # noqa: E402
+from neural_rx_b200.pusch import build_grid  # noqa: E402
+from neural_rx_b200.synth import make_slots  # noqa: E402
+from neural_rx_b200.weights import load_weights, random_weights  # noqa: E402
+
+WORKLOAD = "nrx_large"
+METRIC = "nrx_slots_per_s"
+UNIT = "slots/s"
+
+
+def _weights(cfg):
+    for d in (os.path.join(ROOT, "weights"), "/root/reference/weights"):
+        p = os.path.join(d, f"{cfg.label}_weights")
+        if os.path.exists(p):
+            return load_weights(cfg, p), "shipped weight file"
+    return random_weights(cfg, seed=0), "random-init weights"
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1388.1), d.get("hbm_gbs", 6523.3), "MEASURED_PEAKS.json (sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_slots_per_s(cfg, weights, grid, sb, n_slots: int, threads: int):
+    """Time the CPU restatement of the path (oracle) on ``n_slots`` slots; returns (slots/s, seconds)."""
+    import torch
+    from oracle import nrx_oracle as O
+    from tests.common import oracle_arch
+    torch.set_num_threads(threads)
+    arch = oracle_arch(cfg)
+    net = O.bind_weights(arch, weights.to_list())
+    tables = dict(nn=grid.nn_index, pe=grid.pos_enc)
+    O.receiver_forward(net, arch, sb.y[:1], grid.pilots, grid.pilot_mask, sb.active_tx[:1], tables=tables)  # warm-up
+    t0 = time.perf_counter()
+    for i in range(n_slots):
+        j = i % sb.y.shape[0]
+        O.receiver_forward(net, arch, sb.y[j:j + 1], grid.pilots, grid.pilot_mask, sb.active_tx[j:j + 1], tables=tables)
+    dt = time.perf_counter() - t0
+    return n_slots / dt, dt
+
+
+def run_reference(args, rank):
+    """Reference arm: CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cfg = get_config(WORKLOAD)
+    weights, wsrc = _weights(cfg)
+    grid = build_grid(cfg)
+    sb = make_slots(cfg, grid, batch=2, ebno_db=4.0, seed=2024)
+    cores = os.cpu_count() or 1
+    per_step = 2                       # bounded sample: 2 of the 30 slots of a step
+    for _ in range(args.warmup):
+        oracle_slots_per_s(cfg, weights, grid, sb, 1, cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        _, dt = oracle_slots_per_s(cfg, weights, grid, sb, per_step, cores)
+        t_total += dt
+        n_total += per_step
+    v = n_total / t_total
+    sample = f"{per_step} slots per step x {args.steps} steps of the {cfg.batch_size_eval}-slot batch ({wsrc})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cfg.batch_size_eval / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "nrx_large.cfg: 132 PRB x 14 symbols, 2 UEs, 4 rx antennas, 16-QAM, batch 30",
+                   "note": "TensorFlow/Sionna reference cannot run offline; CPU restatement (oracle port) timed"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def latency_percentiles(eng, y1, act1, n: int = 200):
+    import torch
+    for _ in range(10):
+        eng.forward(y1, act1, want=("llr", "h_hat_refined"))
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.forward(y1, act1, want=("llr", "h_hat_refined"))
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts = np.sort(np.asarray(ts))
+    return {"p50": float(ts[len(ts) // 2]), "p99": float(ts[min(len(ts) - 1, int(0.99 * len(ts)))]), "n": n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots-per-pass", type=int, default=int(os.environ.get("NRX_SLOTS_PER_PASS", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from neural_rx_b200.distributed import max_over_ranks, sum_counters
+    from neural_rx_b200.engine import NrxEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the receiver has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = get_config(WORKLOAD)
+    weights, wsrc = _weights(cfg)
+    grid = build_grid(cfg)
+    B = cfg.batch_size_eval
+    eng = NrxEngine(cfg, weights, grid, device=local_rank)
+    if args.slots_per_pass:
+        eng.set_slots_per_pass(args.slots_per_pass)
+
+    # distinct synthetic batches per rank; rotating over NBUF x 21 MB of inputs (> 126 MB L2)
+    NBUF = 8
+    base = make_slots(cfg, grid, batch=B, ebno_db=np.linspace(-2, 6, B), seed=1000 + rank)
+    rng = np.random.default_rng(77 + rank)
+    ys_host, ys = [], []
+    for i in range(NBUF):
+        yi = base.y if i == 0 else (base.y * np.exp(1j * rng.uniform(0, 2 * np.pi)) +
+                                    0.01 * (rng.standard_normal(base.y.shape) + 1j * rng.standard_normal(base.y.shape))
+                                    ).astype(np.complex64)
+        ys_host.append(np.ascontiguousarray(yi))
+        ys.append(torch.as_tensor(yi).to(dev))
+    act = torch.as_tensor(base.active_tx).to(dev)
+    want = ("llr", "h_hat_refined")
+    outs = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----------------------------------------------------
+    for i in range(args.warmup):
+        eng.forward(ys[i % NBUF], act, want=want, out=outs)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for i in range(args.steps):
+            eng.forward(ys[i % NBUF], act, want=want, out=outs)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms)
+    value = world * B * args.steps / (ms * 1e-3)
+    launches = eng.launches_per_forward(B) * args.steps
+
+    # ---- per-kernel durations (second pass over the same steps, events around every launch) ------
+    eng.set_profiling(True)
+    for i in range(args.steps):
+        eng.forward(ys[i % NBUF], act, want=want, out=outs)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    peak_tf, peak_hbm, peak_src = _measured_peaks()
+    P_step = B * grid.num_tx * grid.num_subcarriers * grid.num_ofdm_symbols     # user-REs per step
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    # algorithmic FLOPs of the dominant kernel per launch = 2 * MACs/pixel of that layer * pixels per launch
+    cin0, ds, hid = 4 * cfg.num_rx_antennas + 2, cfg.d_s, cfg.num_units_state[0][0]
+    mac_layer = {"sep_128x128": 9 * hid + hid * hid, "sep_32x128": 9 * cin0 + cin0 * hid,
+                 "sep_128x64_init_out": 9 * hid + hid * ds, "sep_128x64_update_out": 9 * hid + hid * ds,
+                 "agg": 2 * ds * cfg.num_units_agg[0][0],
+                 "readout": 2 * ds * cfg.num_units_readout[0]
+                 + cfg.num_units_readout[0] * (cfg.num_bits_per_symbol[0] + 2 * cfg.num_rx_antennas)}
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    roof = None
+    if dom in mac_layer and prof[dom]["launches"]:
+        n_l = prof[dom]["launches"]
+        launches_per_step = n_l / args.steps
+        # every launch of a layer class covers all pixels of one pass; passes per step * layers per pass = launches
+        passes = (B + (args.slots_per_pass or B) - 1) // (args.slots_per_pass or B)
+        pixels_per_launch = P_step / passes
+        flops_per_launch = 2.0 * mac_layer[dom] * pixels_per_launch
+        dur_s = prof[dom]["ms"] * 1e-3 / n_l
+        achieved = flops_per_launch / dur_s / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "launch_us": dur_s * 1e6, "launches_per_step": launches_per_step,
+                "share_of_kernel_time": prof[dom]["ms"] / max(total_kernel_ms, 1e-9)}
+    whole = {"achieved_tflops": eng.flops_per_slot() * value / world / 1e12,
+             "frac_of_peak": eng.flops_per_slot() * value / world / 1e12 / peak_tf}
+
+    # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
+    for i in range(2):
+        eng.forward_host(ys_host[i % NBUF], base.active_tx, want=want)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = eng.forward_host(ys_host[i % NBUF], base.active_tx, want=want)
+    barrier()
+    dt = time.perf_counter() - t0
+    dt = max_over_ranks(dt)
+    h2d = ys_host[0].nbytes + base.active_tx.nbytes
+    d2h = sum(v.nbytes for v in res.values())
+    e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h)}
+
+    # ---- counters over NCCL (the only collective: slots processed per rank) -------------------------
+    slots_done = sum_counters({"slots": B * args.steps})["slots"]
+
+    if rank == 0:
+        extra = {}
+        if not args.no_latency:
+            lat = {}
+            y1, a1 = ys[0][:1].contiguous(), act[:1].contiguous()
+            lat["nrx_large"] = latency_percentiles(eng, y1, a1)
+            cfg_rt = get_config("nrx_rt")
+            w_rt, _ = _weights(cfg_rt)
+            eng_rt = NrxEngine(cfg_rt, w_rt, grid, device=local_rank)
+            lat["nrx_rt"] = latency_percentiles(eng_rt, y1, a1)
+            eng_rt.close()
+            extra["latency_us"] = lat
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu = 8
+            v_cpu, dt_cpu = oracle_slots_per_s(cfg, weights, grid, base, n_cpu, cores)
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu} slots of the same batch through oracle/nrx_oracle.py (PyTorch-CPU fp32), {dt_cpu:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": f"synthetic ({wsrc})",
+            "config": {"workload": "nrx_large.cfg: 132 PRB x 14 symbols, 2 UEs, 4 rx antennas, 16-QAM, "
+                                   f"{cfg.num_nrx_iter} CGNN iterations, batch {B} slots per GPU per step",
+                       "slots_per_pass": args.slots_per_pass or B,
+                       "l2": f"inputs rotate over {NBUF} distinct batches ({NBUF * ys_host[0].nbytes / 1e6:.0f} MB > 126 MB L2)",
+                       "parallelism": f"slot-sharded x{world}, no data-path collective"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "whole_path": whole,
+            "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+            "cpu_baseline": cpu, "clocks": clk.summary(), "slots_processed": slots_done,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

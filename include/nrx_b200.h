@@ -119,6 +119,22 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
  * num_it (sum of weight elements, biases excluded — SURVEY.md App. A.6). */
 int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);
 
+/* Per-kernel timing for the roofline report (bench.py): with profiling enabled nrx_forward brackets
+ * every launch with CUDA events on the launching stream; nrx_get_profile synchronises, adds the
+ * elapsed milliseconds and launch counts of each kernel class since the last call into
+ * ms[NRX_NUM_KERNEL_CLASSES] / launches[NRX_NUM_KERNEL_CLASSES] and resets the record. */
+#define NRX_K_POWER 0        /* input power partial sums                          */
+#define NRX_K_PREP 1         /* LS + FOCC + NN interpolation + normalisation      */
+#define NRX_K_SEP_IN 2       /* sep-conv  32 -> 128 (first StateInit layer)       */
+#define NRX_K_SEP_HID 3      /* sep-conv 128 -> 128 (+ReLU)                       */
+#define NRX_K_SEP_INIT_OUT 4 /* sep-conv 128 -> d_s, StateInit output             */
+#define NRX_K_SEP_UPD_OUT 5  /* sep-conv 128 -> d_s, UpdateState output + residual */
+#define NRX_K_AGG 6          /* AggregateUserStates MLP + cross-user reduction    */
+#define NRX_K_READOUT 7      /* ReadoutLLRs + ReadoutChEst + RG demapping         */
+#define NRX_NUM_KERNEL_CLASSES 8
+int nrx_set_profiling(nrx_engine* e, int32_t enable);
+int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
+
 const char* nrx_last_error(void);
 const char* nrx_version(void);
 

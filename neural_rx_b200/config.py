@@ -202,12 +202,13 @@ def _large(**kw) -> NrxConfig:
 #: whenever /root/reference is present)
 PRESETS = {
     "nrx_rt": _rt(label="nrx_rt"),
-    "nrx_rt_64qam": _rt(label="nrx_rt_64qam", mcs_index=(19,), snr_db_eval_max=10.0),
+    "nrx_rt_64qam": _rt(label="nrx_rt_64qam", mcs_index=(19,), snr_db_eval_max=12.0),
     "nrx_rt_var_mcs": _rt(label="nrx_rt_var_mcs", mcs_index=(9, 14), snr_db_eval_min=-3.0),
     "nrx_large": _large(),
-    "nrx_large_qpsk": _large(label="nrx_large_qpsk", mcs_index=(9,)),
+    "nrx_large_qpsk": _large(label="nrx_large_qpsk", mcs_index=(9,), snr_db_eval_min=-3.0, snr_db_eval_max=8.0),
     "nrx_large_64qam": _large(label="nrx_large_64qam", mcs_index=(19,), snr_db_eval_max=10.0),
-    "nrx_large_var_mcs": _large(label="nrx_large_var_mcs", mcs_index=(9, 14), snr_db_eval_min=-3.0),
+    "nrx_large_var_mcs": _large(label="nrx_large_var_mcs", mcs_index=(9, 14), snr_db_eval_min=-3.0,
+                                snr_db_eval_max=8.0),
     "nrx_large_var_mcs_64qam_masking": _large(
         label="nrx_large_var_mcs_64qam_masking", mcs_index=(9, 14, 19), mcs_var_mcs_masking=True,
         snr_db_eval_min=-3.0, snr_db_eval_max=10.0),

@@ -75,6 +75,11 @@ struct nrx_engine {
     int n_pilot_slots = 0;
     int64_t mac_fixed[NRX_MAX_IO] = {0};            // StateInit + readouts per head
     int64_t mac_per_it = 0;
+    // per-kernel event timing (nrx_set_profiling)
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
     // host-call staging (nrx_forward_host)
     cudaStream_t stream = nullptr;
     void* h_pin = nullptr;
@@ -148,8 +153,43 @@ std::vector<int> identity_map(int n) {
     return m;
 }
 
+cudaEvent_t take_event(nrx_engine* e) {
+    if (!e->event_pool.empty()) {
+        cudaEvent_t ev = e->event_pool.back();
+        e->event_pool.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+}
+
+// RAII bracket: records an event pair around one launch when profiling is on
+struct Timed {
+    nrx_engine* e;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int cls;
+    Timed(nrx_engine* e_, cudaStream_t st_, int cls_) : e(e_), st(st_), cls(cls_) {
+        if (e->profiling) {
+            a = take_event(e);
+            b = take_event(e);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~Timed() {
+        if (a) {
+            cudaEventRecord(b, st);
+            e->spans.push_back({cls, a, b});
+        }
+    }
+};
+
 template <int KPAD, int NPAD, int MODE>
-void launch_sep(const nrx_engine* e, cudaStream_t st, SepParams p) {
+void launch_sep(nrx_engine* e, cudaStream_t st, SepParams p) {
+    constexpr int cls = KPAD == 32 ? NRX_K_SEP_IN : MODE == kHidden ? NRX_K_SEP_HID
+                        : MODE == kInitOut ? NRX_K_SEP_INIT_OUT : NRX_K_SEP_UPD_OUT;
+    Timed t(e, st, cls);
     const int grid = p.num_tiles < 2 * e->num_sms ? p.num_tiles : 2 * e->num_sms;
     nrx_sepconv_kernel<KPAD, NPAD, MODE><<<grid, kThreads, SepSmem<KPAD, NPAD>::kTotal, st>>>(p);
 }
@@ -177,6 +217,8 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->d_ws);
     if (e->h_pin) cudaFreeHost(e->h_pin);
     if (e->stream) cudaStreamDestroy(e->stream);
+    for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
     delete e;
     return NRX_OK;
 }
@@ -372,6 +414,28 @@ int nrx_get_num_it(const nrx_engine* e, int32_t* num_it) {
     return NRX_OK;
 }
 
+int nrx_set_profiling(nrx_engine* e, int32_t enable) {
+    if (!e) return fail(NRX_ERR_INVALID, "null engine");
+    e->profiling = enable != 0;
+    return NRX_OK;
+}
+
+int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
+    if (!e || !ms || !launches) return fail(NRX_ERR_INVALID, "nrx_get_profile: null argument");
+    NRX_CUDA(cudaSetDevice(e->device));
+    for (auto& s : e->spans) {
+        NRX_CUDA(cudaEventSynchronize(s.b));
+        float t = 0.f;
+        NRX_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.cls] += t;
+        launches[s.cls] += 1;
+        e->event_pool.push_back(s.a);
+        e->event_pool.push_back(s.b);
+    }
+    e->spans.clear();
+    return NRX_OK;
+}
+
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots) {
     if (!e || slots < 0) return fail(NRX_ERR_INVALID, "slots_per_pass must be >= 0");
     e->slots_per_pass = slots;
@@ -422,7 +486,10 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
 
     const int F = d.num_subcarriers, U = d.max_num_tx, N = d.num_rx_ant;
     const int per_slot = F * kT;
-    nrx_power_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(static_cast<const float2*>(y), partial, N * per_slot);
+    {
+        Timed t(e, st, NRX_K_POWER);
+        nrx_power_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(static_cast<const float2*>(y), partial, N * per_slot);
+    }
 
     const int bp_max = pass_slots(e, batch);
     for (int b0 = 0; b0 < batch; b0 += bp_max) {
@@ -437,7 +504,10 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
         pp.z0 = z0;
         pp.h_ls = h_hat_ls;
         pp.F = F; pp.U = U; pp.N = N; pp.n_pilot_slots = e->n_pilot_slots; pp.b0 = b0; pp.bp = bp;
-        nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
+        {
+            Timed t(e, st, NRX_K_PREP);
+            nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
+        }
 
         SepParams sp{};
         sp.F = F; sp.U = U; sp.d_s = d.d_s;
@@ -468,11 +538,14 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             ap.num_tiles = ap.tiles_per_b * bp;
             const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
             const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
+            {
+            Timed t(e, st, NRX_K_AGG);
             switch (U) {
                 case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
                 case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
                 case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
                 default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+            }
             }
             const auto& L = e->upd_layers[it];
             sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
@@ -501,7 +574,10 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
         rp.num_tiles = rp.tiles_per_bu * BU;
         rp.default_head = llr_head;
         const int grid = rp.num_tiles < e->num_sms ? rp.num_tiles : e->num_sms;
-        nrx_readout_kernel<<<grid, kThreads, kRoSmem, st>>>(rp);
+        {
+            Timed t(e, st, NRX_K_READOUT);
+            nrx_readout_kernel<<<grid, kThreads, kRoSmem, st>>>(rp);
+        }
     }
     NRX_CUDA(cudaGetLastError());
     return NRX_OK;

@@ -24,8 +24,11 @@ NRX_MAX_DMRS = 4
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_launches_per_forward",
-    "nrx_mac_per_pixel", "nrx_last_error", "nrx_version",
+    "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
+
+KERNEL_CLASSES = ("power", "prep", "sep_32x128", "sep_128x128", "sep_128x64_init_out",
+                  "sep_128x64_update_out", "agg", "readout")
 
 
 class NrxError(RuntimeError):
@@ -82,6 +85,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                      ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p]
     lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
+    lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_get_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_last_error.restype = ctypes.c_char_p
     lib.nrx_version.restype = ctypes.c_char_p
     for name in EXPORTED_SYMBOLS:
@@ -191,6 +196,16 @@ class NrxEngine:
         v = ctypes.c_int64()
         self._check(self._lib.nrx_mac_per_pixel(self._h, int(llr_head), ctypes.byref(v)))
         return v.value
+
+    def set_profiling(self, enable: bool) -> None:
+        self._check(self._lib.nrx_set_profiling(self._h, int(bool(enable))))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-class CUDA-event time (ms) and launch count since the last call."""
+        ms = (ctypes.c_double * len(KERNEL_CLASSES))()
+        n = (ctypes.c_int64 * len(KERNEL_CLASSES))()
+        self._check(self._lib.nrx_get_profile(self._h, ms, n))
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(KERNEL_CLASSES)}
 
     def flops_per_slot(self, llr_head: int = 0) -> float:
         """Algorithmic FLOPs of one slot: 2 * U * F * T * MAC_per_pixel."""

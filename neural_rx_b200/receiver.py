@@ -1,0 +1,134 @@
+"""Receiver-facing API: the reference's object interface for the neural-receiver hot path, backed
+by the CUDA engine.
+
+Mirrors (names, argument meaning, error behaviour):
+
+* ``NeuralPUSCHReceiver(sys_parameters, training=False)`` — ``utils/neural_rx.py:1384-1603``;
+  inference call ``receiver((y, active_tx), no, mcs_arr_eval=[0], mcs_ue_mask_eval=None)``
+  (``:1544-1603``; ``no`` never influences the LLRs, it only fed the discarded LS error variance).
+  The reference then runs Sionna's ``TBDecoder`` on the LLRs (``:1600``); the transport-block
+  chain is third-party code outside this hot path, so the first tuple element
+  is the LLR tensor ``[B, U, n_coded_bits]`` that the decoder would consume and the CRC status
+  is ``None``.
+* ``CGNNOFDM`` LLR-level call — ``utils/neural_rx.py:813-881``:
+  ``receiver.llrs((y, active_tx), mcs_arr_eval, mcs_ue_mask_eval)`` -> ``(llr, h_hat_refined)``.
+* ``num_it`` property with the reference's assertion (``:532-542``).
+* ``load_weights(receiver, path)`` — ``utils/utils.py:53-70``.
+
+``sys_parameters`` is an :class:`~neural_rx_b200.config.NrxConfig` (the subset of the reference's
+``Parameters`` object that the hot path reads), a preset name or a cfg file path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .config import NrxConfig, get_config
+from .engine import NrxEngine
+from .pusch import PuschGrid, build_grid
+from .weights import NrxWeights, load_weights as _load_weight_file, random_weights
+
+
+class NeuralPUSCHReceiver:
+    def __init__(self, sys_parameters: Union[NrxConfig, str], training: bool = False,
+                 weights: Optional[NrxWeights] = None, grid: Optional[PuschGrid] = None,
+                 device: int = 0, **kwargs):
+        if training:
+            raise NotImplementedError("the B200 engine implements the inference path only")
+        cfg = get_config(sys_parameters) if isinstance(sys_parameters, str) else sys_parameters
+        cfg.validate()
+        self._sys_parameters = cfg
+        self._grid = build_grid(cfg) if grid is None else grid
+        self._device = device
+        self._num_it = cfg.num_nrx_iter_eval
+        self._engine: Optional[NrxEngine] = None
+        # like Keras, the layers exist (randomly initialised) until load_weights() is called
+        self.set_weights(random_weights(cfg) if weights is None else weights)
+
+    # ---- weights ----------------------------------------------------------------------------
+    def set_weights(self, weights: NrxWeights) -> None:
+        if self._engine is not None:
+            self._engine.close()
+        self._weights = weights
+        self._engine = NrxEngine(self._sys_parameters, weights, self._grid, self._device)
+        self._engine.num_it = self._num_it
+
+    def get_weights(self):
+        return self._weights.to_list()
+
+    # ---- properties -----------------------------------------------------------------------------
+    @property
+    def engine(self) -> NrxEngine:
+        return self._engine
+
+    @property
+    def grid(self) -> PuschGrid:
+        return self._grid
+
+    @property
+    def num_it(self) -> int:
+        return self._num_it
+
+    @num_it.setter
+    def num_it(self, val: int) -> None:
+        # utils/neural_rx.py:537-542
+        assert 1 <= val <= self._sys_parameters.num_nrx_iter, "Invalid number of iterations"
+        self._num_it = int(val)
+        self._engine.num_it = self._num_it
+
+    # ---- calls ------------------------------------------------------------------------------------
+    def _indices(self, batch: int, mcs_arr_eval: Sequence[int], mcs_ue_mask_eval, per_user_heads: bool):
+        cfg = self._sys_parameters
+        U = self._grid.num_tx
+        head = int(mcs_arr_eval[0])
+        if not 0 <= head < cfg.num_mcss_supported:
+            raise ValueError("mcs_arr_eval index out of range")
+        io_index = head_index = None
+        if mcs_ue_mask_eval is not None:
+            m = np.asarray(mcs_ue_mask_eval, dtype=np.float32).reshape(-1, U, cfg.num_mcss_supported)
+            m = np.broadcast_to(m, (batch, U, cfg.num_mcss_supported))
+            if not np.all((m == 0) | (m == 1)) or not np.all(m.sum(-1) == 1):
+                raise ValueError("mcs_ue_mask_eval must be one-hot over the supported MCSs")
+            sel = np.argmax(m, axis=-1).astype(np.int32)
+            if not cfg.mcs_var_mcs_masking:
+                io_index = sel                       # one StateInit stack per MCS (:562-569)
+            if per_user_heads:
+                head_index = np.zeros_like(sel) if cfg.mcs_var_mcs_masking else sel
+        llr_head = 0 if cfg.mcs_var_mcs_masking else head
+        out_bits = None
+        if not per_user_heads:
+            out_bits = cfg.num_bits_per_symbol[head]   # masking mode: slice [..., :bits] (:586-588)
+        return io_index, head_index, llr_head, out_bits
+
+    def llrs(self, inputs: Tuple, mcs_arr_eval: Sequence[int] = (0,), mcs_ue_mask_eval=None,
+             per_user_heads: bool = False, want: Sequence[str] = ("llr", "h_hat_refined", "h_hat")):
+        """LLR-level call (``CGNNOFDM.forward`` inference branch).  ``inputs = (y, active_tx)``,
+        NumPy arrays on the host or torch CUDA tensors.  Returns a dict with the requested
+        outputs (``llr`` [B,U,n_coded_bits] of head ``mcs_arr_eval[0]`` for every user — the
+        reference's behaviour — or, with ``per_user_heads=True``, each user's own head padded to
+        the widest constellation)."""
+        y, active_tx = inputs
+        B = int(y.shape[0])
+        io_index, head_index, llr_head, out_bits = self._indices(B, mcs_arr_eval, mcs_ue_mask_eval, per_user_heads)
+        if isinstance(y, np.ndarray):
+            return self._engine.forward_host(y, np.asarray(active_tx), io_index, head_index, llr_head, out_bits, want)
+        import torch
+        dev = y.device
+        t = lambda a: None if a is None else torch.as_tensor(a, device=dev)
+        out = self._engine.forward(y, torch.as_tensor(active_tx, device=dev), t(io_index), t(head_index),
+                                   llr_head, out_bits, want)
+        return {k: v for k, v in out.items() if not k.startswith("_")}
+
+    def __call__(self, inputs: Tuple, no=None, mcs_arr_eval: Sequence[int] = (0,), mcs_ue_mask_eval=None):
+        """``NeuralPUSCHReceiver.forward`` inference branch: returns
+        ``(llr, h_hat_refined, h_hat, tb_crc_status=None)`` — see the module doc-string."""
+        out = self.llrs(inputs, mcs_arr_eval, mcs_ue_mask_eval)
+        return out["llr"], out["h_hat_refined"], out["h_hat"], None
+
+    forward = __call__
+
+
+def load_weights(receiver: NeuralPUSCHReceiver, model_path: str) -> None:
+    """``utils.load_weights(model, path)``: unpickle the Keras weight list and set it."""
+    receiver.set_weights(_load_weight_file(receiver._sys_parameters, model_path))

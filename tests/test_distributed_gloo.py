@@ -1,0 +1,63 @@
+"""CPU test of the multi-GPU plumbing with world_size 2 over gloo: slot sharding covers every slot
+exactly once and the counter all-reduce / max-over-ranks give every rank the global result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neural_rx_b200.distributed import error_counters, max_over_ranks, slot_shard, sum_counters
+
+
+def test_slot_shard_partitions():
+    for n in (0, 1, 7, 30, 31):
+        for world in (1, 2, 4, 8):
+            blocks = [slot_shard(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        slot_shard(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)                       # same data on every rank, sharded by slot
+    llr = rng.standard_normal((9, 2, 64)).astype(np.float32)
+    bits = rng.integers(0, 2, (9, 2, 64)).astype(np.uint8)
+    act = np.ones((9, 2), np.float32)
+    act[4, 1] = 0
+    lo, hi = slot_shard(9, rank, world)
+    tot = sum_counters(error_counters(llr[lo:hi], bits[lo:hi], act[lo:hi]))
+    q.put((rank, tot, max_over_ranks(1.0 + rank)))
+    dist.destroy_process_group()
+
+
+def test_counters_world_size_2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    llr = rng.standard_normal((9, 2, 64)).astype(np.float32)
+    bits = rng.integers(0, 2, (9, 2, 64)).astype(np.uint8)
+    act = np.ones((9, 2), np.float32)
+    act[4, 1] = 0
+    want = error_counters(llr, bits, act)
+    for _, tot, mx in res:
+        assert tot == want and tot["slots"] == 9
+        assert mx == 2.0
