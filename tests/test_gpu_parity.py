@@ -3,7 +3,7 @@ on the same seeded synthetic slots.
 
 Tolerances (BASELINE.json north_star): LLR relative L2 <= 1e-2 vs the exact fp32 oracle and
 hard-decision agreement >= 99.9 %.  A second, tighter comparison runs against the oracle with the
-engine's rounding points emulated (fp16 operands, fp32 GEMM accumulation): <= 2.5e-3 — a layout or
+engine's rounding points emulated (fp16 operands, fp32 GEMM accumulation): <= 4e-3 — a layout or
 indexing bug shows up there long before it reaches the headline tolerance.
 """
 import numpy as np
@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_EXACT = 1e-2       # north-star tolerance
 TOL_AGREE = 0.999
-TOL_EMUL = 2.5e-3      # vs the oracle with the engine's rounding points emulated
+TOL_EMUL = 4e-3        # vs the oracle with the engine's rounding points emulated
 
 
 def _engine(cfg, weights, grid):
