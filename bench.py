@@ -253,6 +253,8 @@ def main():
     cin0, ds, hid = 4 * cfg.num_rx_antennas + 2, cfg.d_s, cfg.num_units_state[0][0]
     mac_layer = {"sep_128x128": 9 * hid + hid * hid, "sep_32x128": 9 * cin0 + cin0 * hid,
                  "sep_128x64_init_out": 9 * hid + hid * ds, "sep_128x64_update_out": 9 * hid + hid * ds,
+                 "stack_init": (9 + hid) * cin0 + (9 + hid) * hid + (9 + ds) * hid,
+                 "stack_update": (9 + hid) * (2 * ds + 2) + (9 + hid) * hid + (9 + ds) * hid,
                  "agg": 2 * ds * cfg.num_units_agg[0][0],
                  "readout": 2 * ds * cfg.num_units_readout[0]
                  + cfg.num_units_readout[0] * (cfg.num_bits_per_symbol[0] + 2 * cfg.num_rx_antennas)}

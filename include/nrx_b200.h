@@ -87,6 +87,13 @@ int nrx_get_num_it(const nrx_engine* e, int32_t* num_it);
  * 0 = whole batch in one pass. */
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
 
+/* Execution plan of the sep-conv stacks (StateInit :61-132, UpdateState :210-270):
+ *   fused != 0 (default): one kernel per stack, the two 128-channel hidden activations stay in
+ *                         shared memory (line-buffer fusion along the subcarrier axis);
+ *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
+ * Both plans compute the same function; the layer-wise plan is kept as a cross-check. */
+int nrx_set_fused(nrx_engine* e, int32_t fused);
+
 /* Bytes of device scratch nrx_forward needs for `batch` slots. */
 int nrx_workspace_bytes(const nrx_engine* e, int32_t batch, size_t* bytes);
 
@@ -131,7 +138,9 @@ int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);
 #define NRX_K_SEP_UPD_OUT 5  /* sep-conv 128 -> d_s, UpdateState output + residual */
 #define NRX_K_AGG 6          /* AggregateUserStates MLP + cross-user reduction    */
 #define NRX_K_READOUT 7      /* ReadoutLLRs + ReadoutChEst + RG demapping         */
-#define NRX_NUM_KERNEL_CLASSES 8
+#define NRX_K_STACK_INIT 8   /* fused StateInit stack (3 sep-convs, hidden tiles on chip)         */
+#define NRX_K_STACK_UPD 9    /* fused UpdateState stack (3 sep-convs + residual)                 */
+#define NRX_NUM_KERNEL_CLASSES 10
 int nrx_set_profiling(nrx_engine* e, int32_t enable);
 int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
 

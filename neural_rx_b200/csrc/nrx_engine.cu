@@ -15,6 +15,7 @@
 
 #include "../../include/nrx_b200.h"
 #include "nrx_kernels.cuh"
+#include "nrx_stack.cuh"
 
 using namespace nrx;
 
@@ -68,6 +69,9 @@ struct nrx_engine {
     std::vector<std::vector<SepLayer>> upd_layers;  // [it][3]
     std::vector<uint8_t*> agg_blobs;                // [it]
     uint8_t* readout_blob = nullptr;                // [n_io] heads
+    uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
+    std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
+    bool fused = true;                              // fused stack kernels (default) vs layer-per-kernel
     int32_t* nn_index = nullptr;
     FoccEntry* focc = nullptr;
     float* pos_enc = nullptr;
@@ -93,7 +97,7 @@ struct nrx_engine {
 namespace {
 
 struct Workspace {
-    size_t partial, z0, h1, h2, abuf, sbuf, total;
+    size_t partial, z0, h1, h2, abuf, sbuf, sbuf2, total;
 };
 
 int pass_slots(const nrx_engine* e, int batch) {
@@ -111,6 +115,7 @@ Workspace layout(const nrx_engine* e, int batch) {
     w.h2 = off;      off = align_up(off + P * 128 * 2, 256);
     w.abuf = off;    off = align_up(off + P * 64 * 2, 256);
     w.sbuf = off;    off = align_up(off + P * 64 * 2, 256);
+    w.sbuf2 = off;   off = align_up(off + P * 64 * 2, 256);
     w.total = off;
     return w;
 }
@@ -118,6 +123,12 @@ Workspace layout(const nrx_engine* e, int batch) {
 template <typename K>
 cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+std::vector<int> identity_map(int n) {
+    std::vector<int> m(n);
+    for (int i = 0; i < n; ++i) m[i] = i;
+    return m;
 }
 
 // Build the device blob of one sep-conv layer position for all stacks.
@@ -147,10 +158,28 @@ int build_sep_layer(SepLayer& L, int n_stacks, const float* const* arrays, const
     return NRX_OK;
 }
 
-std::vector<int> identity_map(int n) {
-    std::vector<int> m(n);
-    for (int i = 0; i < n; ++i) m[i] = i;
-    return m;
+// Weight image of one fused stack (StackSmem<MODE> layout): three pointwise B images, three tap
+// tables [9][K] fp16, biases fp32 [128 | 128 | 64].  `first` indexes the stack's first array
+// (depthwise, pointwise, bias per layer).
+template <int MODE>
+int pack_stack_blob(uint8_t* b, const float* const* arrays, const int64_t* sizes, int first, const int (&widths)[4],
+                    const std::vector<int>& kmap1) {
+    using L = StackSmem<MODE>;
+    const int w_off[3] = {L::oPw1, L::oPw2, L::oPw3}, t_off[3] = {L::oTap1, L::oTap2, L::oTap3};
+    const int kpad[3] = {L::KP1, 128, 128}, npad[3] = {128, 128, 64}, b_off[3] = {0, 128, 256};
+    for (int l = 0; l < 3; ++l) {
+        const int i = first + 3 * l, cin = widths[l], cout = widths[l + 1];
+        if (sizes[i] != int64_t(9) * cin || sizes[i + 1] != int64_t(cin) * cout || sizes[i + 2] != cout)
+            return fail(NRX_ERR_INVALID, "SeparableConv2D(%d->%d) expected at weight index %d", cin, cout, i);
+        const std::vector<int> km = l == 0 ? kmap1 : identity_map(cin);
+        pack_pw(b + w_off[l], arrays[i + 1], cin, cout, npad[l], km);
+        __half* dw = reinterpret_cast<__half*>(b + t_off[l]);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int c = 0; c < cin; ++c) dw[tap * kpad[l] + km[c]] = __float2half(arrays[i][size_t(tap) * cin + c]);
+        float* bias = reinterpret_cast<float*>(b + L::oBias) + b_off[l];
+        for (int n = 0; n < cout; ++n) bias[n] = arrays[i + 2][n];
+    }
+    return NRX_OK;
 }
 
 cudaEvent_t take_event(nrx_engine* e) {
@@ -194,6 +223,24 @@ void launch_sep(nrx_engine* e, cudaStream_t st, SepParams p) {
     nrx_sepconv_kernel<KPAD, NPAD, MODE><<<grid, kThreads, SepSmem<KPAD, NPAD>::kTotal, st>>>(p);
 }
 
+void launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const uint8_t* blob, const float* active,
+                int U, int per_slot, int bp) {
+    AggParams ap{};
+    ap.sbuf = s; ap.abuf = a; ap.wblob = blob; ap.active_tx = active;
+    ap.U = U; ap.rows_per_bu = per_slot;
+    ap.tiles_per_b = (per_slot + 127) / 128;
+    ap.num_tiles = ap.tiles_per_b * bp;
+    const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
+    const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
+    Timed t(e, st, NRX_K_AGG);
+    switch (U) {
+        case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
+        case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
+        case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
+        default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -209,6 +256,8 @@ int nrx_destroy(nrx_engine* e) {
         for (auto& L : it) cudaFree(L.blob);
     for (auto* b : e->agg_blobs) cudaFree(b);
     cudaFree(e->readout_blob);
+    cudaFree(e->stack_init_blob);
+    for (auto* b : e->stack_upd_blobs) cudaFree(b);
     cudaFree(e->nn_index);
     cudaFree(e->focc);
     cudaFree(e->pos_enc);
@@ -272,6 +321,18 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     }
     for (int m = 0; m < d.n_io; ++m)
         for (int l = 0; l < 3; ++l) e->mac_fixed[m] += int64_t(9 + widths_i[l + 1]) * widths_i[l];
+    {
+        using LI = StackSmem<kStackInit>;
+        std::vector<uint8_t> host(size_t(LI::kBlob) * d.n_io, 0);
+        for (int m = 0; m < d.n_io; ++m) {
+            rc = pack_stack_blob<kStackInit>(host.data() + size_t(m) * LI::kBlob, weight_arrays, weight_sizes, 9 * m,
+                                             widths_i, identity_map(widths_i[0]));
+            if (rc) return bail(rc);
+        }
+        if (cudaMalloc(&e->stack_init_blob, host.size()) != cudaSuccess ||
+            cudaMemcpy(e->stack_init_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(NRX_ERR_CUDA, "uploading StateInit stack weights failed"));
+    }
 
     // ---- iterations -----------------------------------------------------------------------------
     int idx = d.n_io * 9;
@@ -280,6 +341,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     const int widths_u[4] = {2 * d.d_s + 2, d.units_state[0], d.units_state[1], d.d_s};
     e->upd_layers.resize(d.num_it);
     e->agg_blobs.resize(d.num_it, nullptr);
+    e->stack_upd_blobs.resize(d.num_it, nullptr);
     for (int it = 0; it < d.num_it; ++it) {
         if (weight_sizes[idx] != int64_t(d.d_s) * d.units_agg || weight_sizes[idx + 1] != d.units_agg ||
             weight_sizes[idx + 2] != int64_t(d.units_agg) * d.d_s || weight_sizes[idx + 3] != d.d_s)
@@ -294,6 +356,15 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             cudaMemcpy(e->agg_blobs[it], host.data(), kAggBlob, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading aggregation weights failed"));
         idx += 4;
+        {
+            using LU = StackSmem<kStackUpdate>;
+            std::vector<uint8_t> sb(LU::kBlob, 0);
+            rc = pack_stack_blob<kStackUpdate>(sb.data(), weight_arrays, weight_sizes, idx, widths_u, upd_map);
+            if (rc) return bail(rc);
+            if (cudaMalloc(&e->stack_upd_blobs[it], sb.size()) != cudaSuccess ||
+                cudaMemcpy(e->stack_upd_blobs[it], sb.data(), sb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(NRX_ERR_CUDA, "uploading UpdateState stack weights failed"));
+        }
         e->upd_layers[it].resize(3);
         for (int l = 0; l < 3; ++l) {
             const int npad = l == 2 ? 64 : 128;
@@ -395,6 +466,8 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_agg_kernel<3>, agg_smem_bytes(3)));
     acc(set_smem(nrx_agg_kernel<4>, agg_smem_bytes(4)));
     acc(set_smem(nrx_readout_kernel, kRoSmem));
+    acc(set_smem(nrx_stack_kernel<kStackInit>, StackSmem<kStackInit>::kTotal));
+    acc(set_smem(nrx_stack_kernel<kStackUpdate>, StackSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
     NRX_CUDA(cudaDeviceSynchronize());
     *out = e;
@@ -436,6 +509,12 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
     return NRX_OK;
 }
 
+int nrx_set_fused(nrx_engine* e, int32_t fused) {
+    if (!e) return fail(NRX_ERR_INVALID, "null engine");
+    e->fused = fused != 0;
+    return NRX_OK;
+}
+
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots) {
     if (!e || slots < 0) return fail(NRX_ERR_INVALID, "slots_per_pass must be >= 0");
     e->slots_per_pass = slots;
@@ -452,7 +531,7 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
     if (!e || !launches || batch < 1) return fail(NRX_ERR_INVALID, "nrx_launches_per_forward: bad argument");
     const int bp = pass_slots(e, batch);
     const int passes = (batch + bp - 1) / bp;
-    *launches = 1 + passes * (1 + 3 + e->num_it * 4 + 1);
+    *launches = e->fused ? 1 + passes * (1 + 1 + e->num_it * 2 + 1) : 1 + passes * (1 + 3 + e->num_it * 4 + 1);
     return NRX_OK;
 }
 
@@ -509,58 +588,74 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
         }
 
-        SepParams sp{};
-        sp.F = F; sp.U = U; sp.d_s = d.d_s;
-        sp.tiles_per_bu = (F + kTileF - 1) / kTileF;
-        sp.num_tiles = sp.tiles_per_bu * BU;
-        sp.pos_enc = e->pos_enc;
-        // ---- StateInit (:107-132), stack per user = one-hot mcs_ue_mask (:562-569) -------------
-        sp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
-        sp.default_stack = llr_head;
-        sp.src0 = z0; sp.src1 = nullptr; sp.C0 = 32; sp.C1 = 0; sp.out = h1;
-        sp.wblob = e->init_layers[0].blob; sp.blob_bytes = e->init_layers[0].blob_bytes;
-        launch_sep<32, 128, kHidden>(e, st, sp);
-        sp.src0 = h1; sp.C0 = 128; sp.out = h2;
-        sp.wblob = e->init_layers[1].blob; sp.blob_bytes = e->init_layers[1].blob_bytes;
-        launch_sep<128, 128, kHidden>(e, st, sp);
-        sp.src0 = h2; sp.out = sbuf;
-        sp.wblob = e->init_layers[2].blob; sp.blob_bytes = e->init_layers[2].blob_bytes;
-        launch_sep<128, 64, kInitOut>(e, st, sp);
-        // ---- CGNN iterations (:576-593) --------------------------------------------------------
-        sp.stack_index = nullptr;
-        sp.default_stack = 0;
-        for (int it = 0; it < e->num_it; ++it) {
-            AggParams ap{};
-            ap.sbuf = sbuf; ap.abuf = abuf; ap.wblob = e->agg_blobs[it];
-            ap.active_tx = active_tx + size_t(b0) * U;
-            ap.U = U; ap.rows_per_bu = per_slot;
-            ap.tiles_per_b = (per_slot + 127) / 128;
-            ap.num_tiles = ap.tiles_per_b * bp;
-            const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
-            const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
+        __half* s_cur = sbuf;
+        if (e->fused) {
+            // ---- fused stacks: StateInit, then per iteration aggregation + fused UpdateState ----
+            __half* s_alt = reinterpret_cast<__half*>(ws + w.sbuf2);
+            StackParams kp{};
+            kp.F = F; kp.U = U; kp.d_s = d.d_s;
+            kp.n_chunks = choose_chunks(BU, F, e->num_sms);
+            kp.num_items = kp.n_chunks * BU;
+            kp.pos_enc = e->pos_enc;
+            const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
+            kp.z0 = z0; kp.s_out = s_cur;
+            kp.wblob = e->stack_init_blob;
+            kp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
+            kp.default_stack = llr_head;
             {
-            Timed t(e, st, NRX_K_AGG);
-            switch (U) {
-                case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
-                case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
-                case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
-                default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+                Timed t(e, st, NRX_K_STACK_INIT);
+                nrx_stack_kernel<kStackInit><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
+            kp.stack_index = nullptr;
+            kp.default_stack = 0;
+            for (int it = 0; it < e->num_it; ++it) {
+                launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
+                kp.a_in = abuf; kp.s_in = s_cur; kp.s_out = s_alt;
+                kp.wblob = e->stack_upd_blobs[it];
+                {
+                    Timed t(e, st, NRX_K_STACK_UPD);
+                    nrx_stack_kernel<kStackUpdate><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+                }
+                __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
             }
-            const auto& L = e->upd_layers[it];
-            sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
-            sp.wblob = L[0].blob; sp.blob_bytes = L[0].blob_bytes;
-            launch_sep<128, 128, kHidden>(e, st, sp);
-            sp.src0 = h1; sp.src1 = nullptr; sp.C0 = 128; sp.C1 = 0; sp.out = h2;
-            sp.wblob = L[1].blob; sp.blob_bytes = L[1].blob_bytes;
+        } else {
+            SepParams sp{};
+            sp.F = F; sp.U = U; sp.d_s = d.d_s;
+            sp.tiles_per_bu = (F + kTileF - 1) / kTileF;
+            sp.num_tiles = sp.tiles_per_bu * BU;
+            sp.pos_enc = e->pos_enc;
+            // ---- StateInit (:107-132), stack per user = one-hot mcs_ue_mask (:562-569) -------------
+            sp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
+            sp.default_stack = llr_head;
+            sp.src0 = z0; sp.src1 = nullptr; sp.C0 = 32; sp.C1 = 0; sp.out = h1;
+            sp.wblob = e->init_layers[0].blob; sp.blob_bytes = e->init_layers[0].blob_bytes;
+            launch_sep<32, 128, kHidden>(e, st, sp);
+            sp.src0 = h1; sp.C0 = 128; sp.out = h2;
+            sp.wblob = e->init_layers[1].blob; sp.blob_bytes = e->init_layers[1].blob_bytes;
             launch_sep<128, 128, kHidden>(e, st, sp);
             sp.src0 = h2; sp.out = sbuf;
-            sp.wblob = L[2].blob; sp.blob_bytes = L[2].blob_bytes;
-            launch_sep<128, 64, kUpdateOut>(e, st, sp);
+            sp.wblob = e->init_layers[2].blob; sp.blob_bytes = e->init_layers[2].blob_bytes;
+            launch_sep<128, 64, kInitOut>(e, st, sp);
+            // ---- CGNN iterations (:576-593) --------------------------------------------------------
+            sp.stack_index = nullptr;
+            sp.default_stack = 0;
+            for (int it = 0; it < e->num_it; ++it) {
+                launch_agg(e, st, sbuf, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
+                const auto& L = e->upd_layers[it];
+                sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
+                sp.wblob = L[0].blob; sp.blob_bytes = L[0].blob_bytes;
+                launch_sep<128, 128, kHidden>(e, st, sp);
+                sp.src0 = h1; sp.src1 = nullptr; sp.C0 = 128; sp.C1 = 0; sp.out = h2;
+                sp.wblob = L[1].blob; sp.blob_bytes = L[1].blob_bytes;
+                launch_sep<128, 128, kHidden>(e, st, sp);
+                sp.src0 = h2; sp.out = sbuf;
+                sp.wblob = L[2].blob; sp.blob_bytes = L[2].blob_bytes;
+                launch_sep<128, 64, kUpdateOut>(e, st, sp);
+            }
         }
         // ---- read-outs + resource-grid demapping (:582-593, :843-858) --------------------------
         ReadoutParams rp{};
-        rp.sbuf = sbuf;
+        rp.sbuf = s_cur;
         rp.wblob = e->readout_blob;
         rp.head_index = head_index ? head_index + size_t(b0) * U : nullptr;
         rp.data_index = e->data_index;

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 2) nrx_sepconv_kernel(SepParams p) {
     static_assert(MODE == kHidden || NPAD == 64, "state output is 64 wide");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* sA = smem + L::offA;
     uint8_t* sW = smem + L::offW;
     const __half* sDw = reinterpret_cast<const __half*>(sW + L::kWpw);
@@ -457,7 +457,7 @@ template <int U>
 __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(AggParams p) {
     constexpr uint32_t TM_COLS = (U <= 1) ? 64 : (U == 2) ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* sA = smem;                      // [U][128 rows][128 B]  state tiles, later the output staging
     uint8_t* sH = smem + U * 16384;          // [U][128][128 B]       hidden activations
     uint8_t* sW = smem + U * 32768;
@@ -617,7 +617,7 @@ constexpr int kRoSmem = 16384 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
 
 __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* sA = smem;                   // [128][128 B]
     uint8_t* sH = smem + 16384;           // 4 slabs [128][128 B]
     uint8_t* sW = smem + 16384 + 65536;

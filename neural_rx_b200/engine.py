@@ -22,13 +22,13 @@ NRX_MAX_DMRS = 4
 
 #: every symbol declared in include/nrx_b200.h
 EXPORTED_SYMBOLS = (
-    "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass",
+    "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_launches_per_forward",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
 
 KERNEL_CLASSES = ("power", "prep", "sep_32x128", "sep_128x128", "sep_128x64_init_out",
-                  "sep_128x64_update_out", "agg", "readout")
+                  "sep_128x64_update_out", "agg", "readout", "stack_init", "stack_update")
 
 
 class NrxError(RuntimeError):
@@ -77,6 +77,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_set_num_it.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_get_num_it.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
     lib.nrx_set_slots_per_pass.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]
     lib.nrx_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p,
                                 i32p, i32p, ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p,
@@ -181,6 +182,10 @@ class NrxEngine:
     def set_slots_per_pass(self, slots: int) -> None:
         self._check(self._lib.nrx_set_slots_per_pass(self._h, int(slots)))
         self._ws = None
+
+    def set_fused(self, fused: bool) -> None:
+        """Fused stack kernels (default) or one kernel per SeparableConv2D layer (cross-check)."""
+        self._check(self._lib.nrx_set_fused(self._h, int(bool(fused))))
 
     def workspace_bytes(self, batch: int) -> int:
         v = ctypes.c_size_t()

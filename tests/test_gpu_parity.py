@@ -22,9 +22,11 @@ TOL_AGREE = 0.999
 TOL_EMUL = 4e-3        # vs the oracle with the engine's rounding points emulated
 
 
-def _engine(cfg, weights, grid):
+def _engine(cfg, weights, grid, fused=True):
     from neural_rx_b200.engine import NrxEngine
-    return NrxEngine(cfg, weights, grid, device=0)
+    eng = NrxEngine(cfg, weights, grid, device=0)
+    eng.set_fused(fused)
+    return eng
 
 
 def _run(eng, sb, **kw):
@@ -83,6 +85,32 @@ def test_llr_parity(label, n_prb, batch, ebno):
     eng.close()
 
 
+@pytest.mark.parametrize("label,n_prb,batch", [("nrx_rt", 4, 3), ("nrx_rt", 1, 2), ("nrx_large", 16, 2),
+                                                ("nrx_rt", 132, 1), ("nrx_rt_var_mcs", 7, 3)])
+def test_fused_equals_layerwise(label, n_prb, batch):
+    """The fused stack kernels (line-buffer fusion, chunked subcarrier axis with run-in) and the
+    layer-per-kernel plan perform the same arithmetic in the same order: identical outputs, and the
+    layer-wise plan itself passes the oracle tolerance."""
+    cfg = get_config(label)
+    weights, _ = get_weights(cfg)
+    grid = build_grid(cfg, n_size_bwp=n_prb)
+    sb = make_slots(cfg, grid, batch=batch, ebno_db=7.0, seed=200 + n_prb)
+    kw = {}
+    if cfg.num_mcss_supported > 1:
+        kw = dict(io_index=np.tile(np.array([[0, 1]], np.int32), (batch, 1)))
+    outs = []
+    for fused in (True, False):
+        eng = _engine(cfg, weights, grid, fused=fused)
+        outs.append(_run(eng, sb, **dict(kw)))
+        eng.close()
+    for k in ("llr", "llr_grid", "h_hat_refined"):
+        assert rel_l2(outs[0][k], outs[1][k]) <= 1e-6, k
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    if cfg.num_mcss_supported == 1:
+        ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx)
+        assert rel_l2(outs[1]["llr"], ref["llr"]) <= TOL_EXACT
+
+
 def test_random_weights_parity():
     """Seeded random-init weights (always available, unlike the staged weight files)."""
     cfg = get_config("nrx_rt")
@@ -114,7 +142,8 @@ def test_active_user_masks(active):
     ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx)
     emu = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx, emu=ENGINE_EMU)
     assert rel_l2(got["llr"], ref["llr"]) <= TOL_EXACT
-    assert rel_l2(got["llr"], emu["llr"]) <= TOL_EMUL
+    # with no active user the LLRs are small residuals of noise: only the headline tolerance applies
+    assert rel_l2(got["llr"], emu["llr"]) <= (TOL_EMUL if act.any() else TOL_EXACT)
     eng.close()
 
 
