@@ -111,13 +111,18 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y,
                 int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
                 float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes);
 
-/* Same call with HOST buffers (pageable or pinned): stages through engine-owned pinned memory,
- * copies host->device, runs, copies the requested outputs back and synchronises.  This is the
- * call a drop-in user of the reference's receiver makes with NumPy arrays. */
+/* Same call with HOST buffers — the call a drop-in user of the reference's receiver makes with
+ * NumPy arrays.  The batch flows through a 3-stage pipeline in chunks of nrx_set_host_chunk slots
+ * (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap on three streams).  Pinned /
+ * registered buffers are DMA'd in place; pageable ones are staged through engine-owned pinned
+ * memory.  Returns after all requested outputs are in the caller's buffers. */
 int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* active_tx,
                      const int32_t* io_index, const int32_t* head_index, int32_t llr_head,
                      int32_t out_bits, float* llr, float* llr_grid, float* h_hat_refined,
                      float* h_hat_ls);
+
+/* Slots per pipeline chunk of nrx_forward_host (0 = default: a third of the batch, at most 16). */
+int nrx_set_host_chunk(nrx_engine* e, int32_t slots);
 
 /* Number of kernels nrx_forward enqueues for `batch` slots with the current settings. */
 int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launches);

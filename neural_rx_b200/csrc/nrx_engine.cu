@@ -85,7 +85,10 @@ struct nrx_engine {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     // host-call staging (nrx_forward_host)
-    cudaStream_t stream = nullptr;
+    static constexpr int kRing = 3;                 // chunks in flight in nrx_forward_host
+    int host_chunk = 0;                             // slots per pipeline chunk (0 = default)
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[kRing] = {}, ev_comp[kRing] = {}, ev_d2h[kRing] = {};
     void* h_pin = nullptr;
     size_t h_pin_bytes = 0;
     void* d_io = nullptr;
@@ -265,7 +268,16 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->d_io);
     cudaFree(e->d_ws);
     if (e->h_pin) cudaFreeHost(e->h_pin);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream) {
+        cudaStreamDestroy(e->stream);
+        cudaStreamDestroy(e->s_h2d);
+        cudaStreamDestroy(e->s_d2h);
+        for (int r = 0; r < nrx_engine::kRing; ++r) {
+            if (e->ev_h2d[r]) cudaEventDestroy(e->ev_h2d[r]);
+            if (e->ev_comp[r]) cudaEventDestroy(e->ev_comp[r]);
+            if (e->ev_d2h[r]) cudaEventDestroy(e->ev_d2h[r]);
+        }
+    }
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     delete e;
@@ -678,6 +690,16 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
     return NRX_OK;
 }
 
+int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {
+    if (!e || slots < 0) return fail(NRX_ERR_INVALID, "host chunk must be >= 0");
+    e->host_chunk = slots;
+    return NRX_OK;
+}
+
+// Host-buffer call: the batch is cut into chunks of `host_chunk` slots that flow through a
+// three-stage pipeline on three streams — H2D of chunk i+1, kernels of chunk i and D2H of chunk
+// i-1 overlap.  Pinned (page-locked / registered) user buffers are DMA'd directly; pageable ones
+// are staged through engine-owned pinned memory chunk by chunk, the memcpy overlapping GPU work.
 int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* active_tx, const int32_t* io_index,
                      const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
                      float* h_hat_refined, float* h_hat_ls) {
@@ -686,34 +708,67 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
     if (out_bits < 1 || out_bits > 16) return fail(NRX_ERR_INVALID, "out_bits out of range");
     const nrx_model_desc& d = e->d;
     NRX_CUDA(cudaSetDevice(e->device));
-    if (!e->stream) NRX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    constexpr int R = nrx_engine::kRing;
+    if (!e->stream) {
+        NRX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        NRX_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        NRX_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+        for (int r = 0; r < R; ++r) {
+            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
+            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_comp[r], cudaEventDisableTiming));
+            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_d2h[r], cudaEventDisableTiming));
+        }
+    }
     const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
-    const size_t BU = size_t(batch) * U;
-    // device / pinned arena layout (256-byte aligned pieces)
+    int C = e->host_chunk > 0 ? e->host_chunk : (batch + 2) / 3;   // default: three chunks in flight, at most 16 slots each
+    if (e->host_chunk <= 0 && C > 16) C = 16;
+    if (C > batch) C = batch;
+    const int n_chunks = (batch + C - 1) / C;
+    // bytes per slot of every stream of data
+    const size_t y_slot = size_t(d.num_rx_ant) * per_slot * 8;
+    float* outs[4] = {llr, llr_grid, h_hat_refined, h_hat_ls};
+    const size_t out_slot[4] = {U * d.num_data_res * out_bits * 4, U * per_slot * out_bits * 4, U * per_slot * N2 * 4,
+                                U * per_slot * N2 * 4};
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool y_pinned = pinned(y);
+    bool out_pinned[4];
+    for (int k = 0; k < 4; ++k) out_pinned[k] = outs[k] && pinned(outs[k]);
+
+    // device arena: [small per-batch inputs][R x (y chunk | 4 output chunks)]
     size_t off = 0;
     auto piece = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_y = piece(size_t(batch) * d.num_rx_ant * per_slot * 8);
-    const size_t o_act = piece(BU * 4);
-    const size_t o_io = piece(BU * 4);
-    const size_t o_head = piece(BU * 4);
-    const size_t in_bytes = off;
-    const size_t o_llr = piece(llr ? BU * d.num_data_res * out_bits * 4 : 0);
-    const size_t o_grid = piece(llr_grid ? BU * per_slot * out_bits * 4 : 0);
-    const size_t o_href = piece(h_hat_refined ? BU * per_slot * N2 * 4 : 0);
-    const size_t o_hls = piece(h_hat_ls ? BU * per_slot * N2 * 4 : 0);
+    const size_t BU = size_t(batch) * U;
+    const size_t o_act = piece(BU * 4), o_io = piece(BU * 4), o_head = piece(BU * 4);
+    const size_t small_bytes = off;
+    size_t o_y[R], o_out[R][4];
+    for (int r = 0; r < R; ++r) {
+        o_y[r] = piece(size_t(C) * y_slot);
+        for (int k = 0; k < 4; ++k) o_out[r][k] = piece(outs[k] ? size_t(C) * out_slot[k] : 0);
+    }
     const size_t total = off;
     if (total > e->d_io_bytes) {
+        NRX_CUDA(cudaDeviceSynchronize());
         cudaFree(e->d_io);
         e->d_io = nullptr;
         e->d_io_bytes = 0;
+        NRX_CUDA(cudaMalloc(&e->d_io, total));
+        e->d_io_bytes = total;
+    }
+    if (total > e->h_pin_bytes) {                      // pinned staging mirrors the device arena
+        NRX_CUDA(cudaDeviceSynchronize());
         if (e->h_pin) cudaFreeHost(e->h_pin);
         e->h_pin = nullptr;
-        NRX_CUDA(cudaMalloc(&e->d_io, total));
+        e->h_pin_bytes = 0;
         NRX_CUDA(cudaMallocHost(&e->h_pin, total));
-        e->d_io_bytes = e->h_pin_bytes = total;
+        e->h_pin_bytes = total;
     }
-    const Workspace w = layout(e, batch);
+    const Workspace w = layout(e, C);
     if (w.total > e->d_ws_bytes) {
+        NRX_CUDA(cudaDeviceSynchronize());
         cudaFree(e->d_ws);
         e->d_ws = nullptr;
         e->d_ws_bytes = 0;
@@ -722,26 +777,51 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
     }
     uint8_t* hp = static_cast<uint8_t*>(e->h_pin);
     uint8_t* dp = static_cast<uint8_t*>(e->d_io);
-    memcpy(hp + o_y, y, size_t(batch) * d.num_rx_ant * per_slot * 8);
     memcpy(hp + o_act, active_tx, BU * 4);
     if (io_index) memcpy(hp + o_io, io_index, BU * 4);
     if (head_index) memcpy(hp + o_head, head_index, BU * 4);
-    NRX_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, e->stream));
-    const int rc = nrx_forward(e, e->stream, batch, dp + o_y, reinterpret_cast<const float*>(dp + o_act),
-                               io_index ? reinterpret_cast<const int32_t*>(dp + o_io) : nullptr,
-                               head_index ? reinterpret_cast<const int32_t*>(dp + o_head) : nullptr, llr_head, out_bits,
-                               llr ? reinterpret_cast<float*>(dp + o_llr) : nullptr,
-                               llr_grid ? reinterpret_cast<float*>(dp + o_grid) : nullptr,
-                               h_hat_refined ? reinterpret_cast<float*>(dp + o_href) : nullptr,
-                               h_hat_ls ? reinterpret_cast<float*>(dp + o_hls) : nullptr, e->d_ws, e->d_ws_bytes);
-    if (rc) return rc;
-    if (total > in_bytes)
-        NRX_CUDA(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, e->stream));
-    NRX_CUDA(cudaStreamSynchronize(e->stream));
-    if (llr) memcpy(llr, hp + o_llr, BU * d.num_data_res * out_bits * 4);
-    if (llr_grid) memcpy(llr_grid, hp + o_grid, BU * per_slot * out_bits * 4);
-    if (h_hat_refined) memcpy(h_hat_refined, hp + o_href, BU * per_slot * N2 * 4);
-    if (h_hat_ls) memcpy(h_hat_ls, hp + o_hls, BU * per_slot * N2 * 4);
+    NRX_CUDA(cudaMemcpyAsync(dp, hp, small_bytes, cudaMemcpyHostToDevice, e->s_h2d));
+
+    auto drain = [&](int i) -> int {                   // chunk i: wait for its D2H, un-stage pageable outputs
+        const int r = i % R, b0 = i * C, n = batch - b0 < C ? batch - b0 : C;
+        NRX_CUDA(cudaEventSynchronize(e->ev_d2h[r]));
+        for (int k = 0; k < 4; ++k)
+            if (outs[k] && !out_pinned[k])
+                memcpy(reinterpret_cast<uint8_t*>(outs[k]) + size_t(b0) * out_slot[k], hp + o_out[r][k], size_t(n) * out_slot[k]);
+        return NRX_OK;
+    };
+    for (int i = 0; i < n_chunks; ++i) {
+        const int r = i % R, b0 = i * C, n = batch - b0 < C ? batch - b0 : C;
+        if (i >= R) { const int rc = drain(i - R); if (rc) return rc; }
+        const uint8_t* ysrc = static_cast<const uint8_t*>(y) + size_t(b0) * y_slot;
+        if (!y_pinned) {
+            memcpy(hp + o_y[r], ysrc, size_t(n) * y_slot);
+            ysrc = hp + o_y[r];
+        }
+        NRX_CUDA(cudaMemcpyAsync(dp + o_y[r], ysrc, size_t(n) * y_slot, cudaMemcpyHostToDevice, e->s_h2d));
+        NRX_CUDA(cudaEventRecord(e->ev_h2d[r], e->s_h2d));
+        NRX_CUDA(cudaStreamWaitEvent(e->stream, e->ev_h2d[r], 0));
+        const int rc = nrx_forward(e, e->stream, n, dp + o_y[r], reinterpret_cast<const float*>(dp + o_act) + size_t(b0) * U,
+                                   io_index ? reinterpret_cast<const int32_t*>(dp + o_io) + size_t(b0) * U : nullptr,
+                                   head_index ? reinterpret_cast<const int32_t*>(dp + o_head) + size_t(b0) * U : nullptr,
+                                   llr_head, out_bits, outs[0] ? reinterpret_cast<float*>(dp + o_out[r][0]) : nullptr,
+                                   outs[1] ? reinterpret_cast<float*>(dp + o_out[r][1]) : nullptr,
+                                   outs[2] ? reinterpret_cast<float*>(dp + o_out[r][2]) : nullptr,
+                                   outs[3] ? reinterpret_cast<float*>(dp + o_out[r][3]) : nullptr, e->d_ws, e->d_ws_bytes);
+        if (rc) return rc;
+        NRX_CUDA(cudaEventRecord(e->ev_comp[r], e->stream));
+        NRX_CUDA(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[r], 0));
+        for (int k = 0; k < 4; ++k)
+            if (outs[k]) {
+                uint8_t* dst = out_pinned[k] ? reinterpret_cast<uint8_t*>(outs[k]) + size_t(b0) * out_slot[k] : hp + o_out[r][k];
+                NRX_CUDA(cudaMemcpyAsync(dst, dp + o_out[r][k], size_t(n) * out_slot[k], cudaMemcpyDeviceToHost, e->s_d2h));
+            }
+        NRX_CUDA(cudaEventRecord(e->ev_d2h[r], e->s_d2h));
+    }
+    for (int i = n_chunks > R ? n_chunks - R : 0; i < n_chunks; ++i) {
+        const int rc = drain(i);
+        if (rc) return rc;
+    }
     return NRX_OK;
 }
 

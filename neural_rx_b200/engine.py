@@ -22,7 +22,7 @@ NRX_MAX_DMRS = 4
 
 #: every symbol declared in include/nrx_b200.h
 EXPORTED_SYMBOLS = (
-    "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused",
+    "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_launches_per_forward",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
@@ -78,6 +78,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_get_num_it.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
     lib.nrx_set_slots_per_pass.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_set_host_chunk.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]
     lib.nrx_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p,
                                 i32p, i32p, ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p,
@@ -187,6 +188,10 @@ class NrxEngine:
         """Fused stack kernels (default) or one kernel per SeparableConv2D layer (cross-check)."""
         self._check(self._lib.nrx_set_fused(self._h, int(bool(fused))))
 
+    def set_host_chunk(self, slots: int) -> None:
+        """Slots per pipeline chunk of the host-buffer call (0 = default)."""
+        self._check(self._lib.nrx_set_host_chunk(self._h, int(slots)))
+
     def workspace_bytes(self, batch: int) -> int:
         v = ctypes.c_size_t()
         self._check(self._lib.nrx_workspace_bytes(self._h, int(batch), ctypes.byref(v)))
@@ -273,7 +278,10 @@ class NrxEngine:
     # ---- host call (NumPy arrays, H2D + D2H inside) --------------------------------------------
     def forward_host(self, y: np.ndarray, active_tx: np.ndarray, io_index=None, head_index=None,
                      llr_head: int = 0, out_bits: Optional[int] = None,
-                     want: Sequence[str] = ("llr", "h_hat_refined", "h_hat")) -> Dict[str, np.ndarray]:
+                     want: Sequence[str] = ("llr", "h_hat_refined", "h_hat"),
+                     out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """NumPy in, NumPy out.  ``out`` may hold preallocated C-contiguous float32 result arrays
+        (e.g. page-locked ones from :func:`pinned_empty`, which are then DMA'd in place)."""
         g, N = self.grid, self.cfg.num_rx_antennas
         y = np.ascontiguousarray(y, dtype=np.complex64)
         B, U = y.shape[0], g.num_tx
@@ -286,7 +294,12 @@ class NrxEngine:
         shapes = {"llr": (B, U, g.num_data_res * bits), "llr_grid": (B, U, g.num_subcarriers, g.num_ofdm_symbols, bits),
                   "h_hat_refined": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N),
                   "h_hat": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N)}
-        res = {k: np.empty(shapes[k], np.float32) for k in want}
+        res = {}
+        for k in want:
+            a = None if out is None else out.get(k)
+            if a is not None and (a.shape != shapes[k] or a.dtype != np.float32 or not a.flags.c_contiguous):
+                raise ValueError(f"out[{k!r}] must be a C-contiguous float32 array of shape {shapes[k]}")
+            res[k] = np.empty(shapes[k], np.float32) if a is None else a
         io = None if io_index is None else np.ascontiguousarray(io_index, dtype=np.int32).reshape(B, U)
         hd = None if head_index is None else np.ascontiguousarray(head_index, dtype=np.int32).reshape(B, U)
         ptr = lambda k: res[k].ctypes.data if k in res else None
@@ -295,3 +308,12 @@ class NrxEngine:
             None if hd is None else hd.ctypes.data, int(llr_head), bits, ptr("llr"), ptr("llr_grid"),
             ptr("h_hat_refined"), ptr("h_hat")))
         return res
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """Page-locked host array (NumPy view of a pinned torch tensor): ``forward_host`` copies such
+    buffers by DMA without staging."""
+    import torch
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.complex64): torch.complex64,
+           np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    return torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
