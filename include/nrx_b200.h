@@ -88,10 +88,15 @@ int nrx_get_num_it(const nrx_engine* e, int32_t* num_it);
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
 
 /* Execution plan of the sep-conv stacks (StateInit :61-132, UpdateState :210-270):
- *   fused != 0 (default): one kernel per stack, the two 128-channel hidden activations stay in
- *                         shared memory (line-buffer fusion along the subcarrier axis);
+ *   fused == 1 (default): one kernel per stack, the two 128-channel hidden activations stay in
+ *                         shared memory (line-buffer fusion along the subcarrier axis); one
+ *                         aggregation kernel per iteration (any number of users);
+ *   fused == 2:           as 1, but with two users the message MLP of AggregateUserStates
+ *                         (:184-188) runs in the tail of the preceding stack, each user reads the
+ *                         other user's message tensor directly and no aggregation kernel is
+ *                         launched (measured on B200: same speed as plan 1);
  *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
- * Both plans compute the same function; the layer-wise plan is kept as a cross-check. */
+ * All plans compute the same function; the others are kept as cross-checks. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);
 
 /* Bytes of device scratch nrx_forward needs for `batch` slots. */

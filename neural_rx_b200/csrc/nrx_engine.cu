@@ -71,7 +71,8 @@ struct nrx_engine {
     uint8_t* readout_blob = nullptr;                // [n_io] heads
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
-    bool fused = true;                              // fused stack kernels (default) vs layer-per-kernel
+    int fused = 1;                                  // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
+                                                    // MLP in their tail (two users only), 0: layer-per-kernel
     int32_t* nn_index = nullptr;
     FoccEntry* focc = nullptr;
     float* pos_enc = nullptr;
@@ -100,7 +101,7 @@ struct nrx_engine {
 namespace {
 
 struct Workspace {
-    size_t partial, z0, h1, h2, abuf, sbuf, sbuf2, total;
+    size_t partial, z0, h1, h2, abuf, abuf2, sbuf, sbuf2, total;
 };
 
 int pass_slots(const nrx_engine* e, int batch) {
@@ -119,6 +120,7 @@ Workspace layout(const nrx_engine* e, int batch) {
     w.abuf = off;    off = align_up(off + P * 64 * 2, 256);
     w.sbuf = off;    off = align_up(off + P * 64 * 2, 256);
     w.sbuf2 = off;   off = align_up(off + P * 64 * 2, 256);
+    w.abuf2 = off;   off = align_up(off + P * 64 * 2, 256);
     w.total = off;
     return w;
 }
@@ -164,6 +166,18 @@ int build_sep_layer(SepLayer& L, int n_stacks, const float* const* arrays, const
 // Weight image of one fused stack (StackSmem<MODE> layout): three pointwise B images, three tap
 // tables [9][K] fp16, biases fp32 [128 | 128 | 64].  `first` indexes the stack's first array
 // (depthwise, pointwise, bias per layer).
+// Message-MLP section of a stack blob: AggregateUserStates Dense(d_s->units_agg), Dense(units_agg->d_s)
+// of the iteration that FOLLOWS the stack (arrays[first..first+3] = k1, b1, k2, b2).
+template <int MODE>
+void pack_stack_agg(uint8_t* b, const float* const* arrays, int first, int d_s, int units_agg) {
+    using L = StackSmem<MODE>;
+    pack_pw(b + L::oAggW1, arrays[first], d_s, units_agg, 64, identity_map(d_s));
+    pack_pw(b + L::oAggW2, arrays[first + 2], units_agg, d_s, 64, identity_map(units_agg));
+    float* bias = reinterpret_cast<float*>(b + L::oAggB);
+    for (int n = 0; n < units_agg; ++n) bias[n] = arrays[first + 1][n];
+    for (int n = 0; n < d_s; ++n) bias[64 + n] = arrays[first + 3][n];
+}
+
 template <int MODE>
 int pack_stack_blob(uint8_t* b, const float* const* arrays, const int64_t* sizes, int first, const int (&widths)[4],
                     const std::vector<int>& kmap1) {
@@ -340,6 +354,10 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             rc = pack_stack_blob<kStackInit>(host.data() + size_t(m) * LI::kBlob, weight_arrays, weight_sizes, 9 * m,
                                              widths_i, identity_map(widths_i[0]));
             if (rc) return bail(rc);
+            // message MLP of iteration 0 (array sizes are validated in the iteration loop below)
+            const int a0 = d.n_io * 9;
+            if (weight_sizes[a0] == int64_t(d.d_s) * d.units_agg && weight_sizes[a0 + 2] == int64_t(d.units_agg) * d.d_s)
+                pack_stack_agg<kStackInit>(host.data() + size_t(m) * LI::kBlob, weight_arrays, a0, d.d_s, d.units_agg);
         }
         if (cudaMalloc(&e->stack_init_blob, host.size()) != cudaSuccess ||
             cudaMemcpy(e->stack_init_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -373,6 +391,12 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             std::vector<uint8_t> sb(LU::kBlob, 0);
             rc = pack_stack_blob<kStackUpdate>(sb.data(), weight_arrays, weight_sizes, idx, widths_u, upd_map);
             if (rc) return bail(rc);
+            if (it + 1 < d.num_it) {     // message MLP of the next iteration (4 agg + 9 sep-conv arrays per iteration)
+                const int an = idx + 9;
+                if (weight_sizes[an] != int64_t(d.d_s) * d.units_agg || weight_sizes[an + 2] != int64_t(d.units_agg) * d.d_s)
+                    return bail(fail(NRX_ERR_INVALID, "AggregateUserStates Dense layers expected at weight index %d", an));
+                pack_stack_agg<kStackUpdate>(sb.data(), weight_arrays, an, d.d_s, d.units_agg);
+            }
             if (cudaMalloc(&e->stack_upd_blobs[it], sb.size()) != cudaSuccess ||
                 cudaMemcpy(e->stack_upd_blobs[it], sb.data(), sb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(NRX_ERR_CUDA, "uploading UpdateState stack weights failed"));
@@ -523,7 +547,8 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    e->fused = fused != 0;
+    if (fused < 0 || fused > 2) return fail(NRX_ERR_INVALID, "fused must be 0, 1 or 2");
+    e->fused = fused;
     return NRX_OK;
 }
 
@@ -543,7 +568,8 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
     if (!e || !launches || batch < 1) return fail(NRX_ERR_INVALID, "nrx_launches_per_forward: bad argument");
     const int bp = pass_slots(e, batch);
     const int passes = (batch + bp - 1) / bp;
-    *launches = e->fused ? 1 + passes * (1 + 1 + e->num_it * 2 + 1) : 1 + passes * (1 + 3 + e->num_it * 4 + 1);
+    *launches = e->fused ? 1 + passes * (1 + 1 + e->num_it * (e->d.max_num_tx == 2 && e->fused == 2 ? 1 : 2) + 1)
+                         : 1 + passes * (1 + 3 + e->num_it * 4 + 1);
     return NRX_OK;
 }
 
@@ -610,25 +636,37 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             kp.num_items = kp.n_chunks * BU;
             kp.pos_enc = e->pos_enc;
             const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
+            // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
+            // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
+            const bool pair = U == 2 && e->fused == 2;
+            __half* sp_cur = abuf;
+            __half* sp_alt = reinterpret_cast<__half*>(ws + w.abuf2);
             kp.z0 = z0; kp.s_out = s_cur;
             kp.wblob = e->stack_init_blob;
             kp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
             kp.default_stack = llr_head;
+            kp.active_tx = active_tx + size_t(b0) * U;
+            kp.pair_agg = 0;
+            kp.sp_out = pair ? sp_cur : nullptr;
             {
                 Timed t(e, st, NRX_K_STACK_INIT);
                 nrx_stack_kernel<kStackInit><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
             kp.stack_index = nullptr;
             kp.default_stack = 0;
+            kp.pair_agg = pair ? 1 : 0;
             for (int it = 0; it < e->num_it; ++it) {
-                launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
-                kp.a_in = abuf; kp.s_in = s_cur; kp.s_out = s_alt;
+                if (!pair)
+                    launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
+                kp.a_in = pair ? sp_cur : abuf; kp.s_in = s_cur; kp.s_out = s_alt;
+                kp.sp_out = pair && it + 1 < e->num_it ? sp_alt : nullptr;
                 kp.wblob = e->stack_upd_blobs[it];
                 {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     nrx_stack_kernel<kStackUpdate><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                 }
                 __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
+                tmp = sp_cur; sp_cur = sp_alt; sp_alt = tmp;
             }
         } else {
             SepParams sp{};
@@ -689,6 +727,16 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
     NRX_CUDA(cudaGetLastError());
     return NRX_OK;
 }
+
+#ifdef NRX_PHASE_TIMING
+// debug build only (tools/phase_timing.py): read and reset the stack kernel's per-phase cycle counters
+int nrx_debug_phase_cycles(unsigned long long* out32) {
+    unsigned long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    return NRX_OK;
+}
+#endif
 
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {
     if (!e || slots < 0) return fail(NRX_ERR_INVALID, "host chunk must be >= 0");

@@ -38,6 +38,12 @@ struct StackParams {
     const __half* s_in;          // update: [BU*F*T][64]  state s | pe | 0   (also the residual)
     __half* s_out;               //         [BU*F*T][64]  new state (never aliases s_in: halo rows of
                                  //                       neighbouring chunks are read while others are written)
+    __half* sp_out;              // [BU*F*T][64] or null: message MLP of the NEXT iteration's AggregateUserStates
+                                 //   applied to the new state, sp = Dense2(relu(Dense1(s_new)))  (:184-188)
+    const float* active_tx;      // [B][U] (pair mode)
+    int pair_agg;                // U == 2 fast path: a_in is the sp tensor written by the previous stack; user u
+                                 //   reads the OTHER user's plane, masked by that user's active flag (:192-204 with
+                                 //   two users: a_u = sp_v * active_v, scale 1)
     const uint8_t* wblob;        // per stack: StackSmem<MODE> weight image
     const int32_t* stack_index;  // [BU] or null
     const float* pos_enc;        // [U][F][T][2]   (init)
@@ -57,11 +63,15 @@ struct StackSmem {
     static constexpr int oPw1 = 0, oPw2 = kPw1, oPw3 = oPw2 + kPw2;
     static constexpr int oTap1 = oPw3 + kPw3, oTap2 = oTap1 + kTap1, oTap3 = oTap2 + kTap;
     static constexpr int oBias = oTap3 + kTap;                         // fp32 [128 | 128 | 64]
-    static constexpr int kBlob = oBias + (128 + 128 + 64) * 4;
+    static constexpr int oAggW1 = align_up_c(oBias + (128 + 128 + 64) * 4, 1024);   // message MLP: W1 image [64 rows][128 B]
+    static constexpr int oAggW2 = oAggW1 + 8192;                       //              W2 image [64 rows][128 B]
+    static constexpr int oAggB = oAggW2 + 8192;                        //              b1[64] | b2[64] fp32
+    static constexpr int kBlob = oAggB + 512;
     static constexpr int offA = align_up_c(kBlob, 1024);               // A operand / fp32 output staging
-    static constexpr int offC1 = offA + 32768;                         // carry of H1 (2 subcarriers)
-    static constexpr int offH = offC1 + kCarryRows * kHRow;            // fresh hidden tile (9 subcarriers)
-    static constexpr int offC2 = offH + kTileRows * kHRow;             // carry of H2
+    static constexpr int offH = offA + 32768;                          // fresh hidden tile (9 subcarriers); 1024-aligned:
+                                                                       //   doubles as the two A slabs of the message MLP
+    static constexpr int offC1 = offH + align_up_c(kTileRows * kHRow, 1024);   // carry of H1 (2 subcarriers)
+    static constexpr int offC2 = offC1 + kCarryRows * kHRow;           // carry of H2
     static constexpr int offZ = offC2 + kCarryRows * kHRow;            // layer-1 input window (11 subcarriers)
     static constexpr int kZRow = MODE == kStackInit ? 64 : 128;
     static constexpr int kZArr = kHaloRows * kZRow;
@@ -124,6 +134,22 @@ __device__ __forceinline__ void dw_slide(const uint8_t* carry, const uint8_t* fr
     tail[1][1] = win[(NFOUT + 1) % 3][2];
 }
 
+// Optional per-phase cycle accounting (build with -DNRX_PHASE_TIMING; tools/phase_timing.py):
+// one thread of CTA 0 accumulates clock64 deltas between the phase boundaries of every step.
+#ifdef NRX_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define NRX_TICK(i)                                                              \
+    do {                                                                         \
+        if (blockIdx.x == 0 && threadIdx.x == 32) {                              \
+            const long long now_ = clock64();                                    \
+            s_phase[i] += (unsigned long long)(now_ - tick_last);                \
+            tick_last = now_;                                                    \
+        }                                                                        \
+    } while (0)
+#else
+#define NRX_TICK(i) do { } while (0)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams p) {
     using L = StackSmem<MODE>;
@@ -136,15 +162,16 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
     uint8_t* sC2 = smem + L::offC2;
     uint8_t* sZ = smem + L::offZ;
     const float* sBias = reinterpret_cast<const float*>(sW + L::oBias);
-    __shared__ uint64_t bar_z, bar_w, bar_mma;
+    __shared__ uint64_t bar_z, bar_w, bar_mma, bar_mlp;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);   // [0,128) layer accumulator, [128,192) / [192,256) message MLP
     if (tid == 0) {
         mbar_init(&bar_z, 1);
         mbar_init(&bar_w, 1);
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_mlp, 1);
         fence_mbar_init();
     }
     {   // rows 126/127 of the A operand are never produced by the depthwise pass: keep them finite
@@ -157,6 +184,12 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
     const uint32_t tbase = tmem_slot;
     uint32_t ph_z = 0, ph_w = 0, ph_mma = 0;
     int loaded_stack = -1;
+#ifdef NRX_PHASE_TIMING
+    __shared__ unsigned long long s_phase[32];
+    if (tid == 32)
+        for (int i = 0; i < 32; ++i) s_phase[i] = 0;
+    long long tick_last = clock64();
+#endif
 
     // ---- depthwise task mapping -------------------------------------------------------------
     // 128-channel layers: thread = (symbol pair ph in 0..6, channel quad qh in 0..31); warp-uniform ph
@@ -177,7 +210,79 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 
     const int q4 = warp & 3, hc = warp >> 2;      // epilogue: TMEM lane quadrant, column half
     const int erow = q4 * 32 + lane;              // accumulator row of this thread
-    const int efl = erow / kT;
+    const int efl = erow / kT, et = erow - (erow / kT) * kT;
+
+    // ---- deferred message-MLP chain of the previous tile (see the end of the step loop) ------------
+    bool pend = false;
+    size_t pend_row0 = 0;
+    int pend_lo = 0, pend_hi = 0;
+    uint32_t ph_mlp = 0;
+    const float* sAggB = reinterpret_cast<const float*>(sW + L::oAggB);
+    // hidden layer of the MLP: TMEM[128..191] -> relu(. + b1) -> fp16 A slab, then issue the second GEMM
+    auto mlp_hidden = [&]() {
+        const int col = hc * 32;
+        float4 bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bq[j] = *reinterpret_cast<const float4*>(sAggB + col + j * 4);
+        mbar_wait(&bar_mlp, ph_mlp);
+        ph_mlp ^= 1;
+        tc_fence_after_sync();
+        float v[32];
+        tmem_ld32(tmem_addr(tbase + 128, q4 * 32, col), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = bq[j >> 2], b1 = bq[(j >> 2) + 1];
+            uint4 o;
+            o.x = pack_relu_half2(v[j] + b0.x, v[j + 1] + b0.y);
+            o.y = pack_relu_half2(v[j + 2] + b0.z, v[j + 3] + b0.w);
+            o.z = pack_relu_half2(v[j + 4] + b1.x, v[j + 5] + b1.y);
+            o.w = pack_relu_half2(v[j + 6] + b1.z, v[j + 7] + b1.w);
+            const int cc = (col + j) >> 3;
+            st_shared_v4(sH + 16384 + erow * 128 + ((cc ^ (erow & 7)) << 4), o);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();                                // hidden slab complete
+        if (tid == 0) {
+            tc_fence_after_sync();
+            umma_gemm_k(tbase + 192, smem_u32(sH + 16384), 16384, smem_u32(sW + L::oAggW2), 8192, 64,
+                        umma_idesc_f16(128, 64), false);
+            umma_commit(&bar_mlp);
+        }
+    };
+    // wait for the second GEMM (its operands live in the hidden-tile region, which the next hidden
+    // epilogue overwrites)
+    auto mlp_wait2 = [&]() {
+        mbar_wait(&bar_mlp, ph_mlp);
+        ph_mlp ^= 1;
+        tc_fence_after_sync();
+    };
+    // output of the MLP: TMEM[192..255] + b2 -> fp16 -> global sp tensor (row per lane)
+    auto mlp_store = [&]() {
+        const int col = hc * 32;
+        float4 bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bq[j] = *reinterpret_cast<const float4*>(sAggB + 64 + col + j * 4);
+        float v[32];
+        tmem_ld32(tmem_addr(tbase + 192, q4 * 32, col), v);
+        tmem_ld_wait();
+        if (erow < kTileRows && erow >= pend_lo && erow < pend_hi) {
+            __half* dst = p.sp_out + (pend_row0 + erow) * 64 + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const float4 b0 = bq[j >> 2], b1 = bq[(j >> 2) + 1];
+                uint4 o;
+                o.x = pack_half2(v[j] + b0.x, v[j + 1] + b0.y);
+                o.y = pack_half2(v[j + 2] + b0.z, v[j + 3] + b0.w);
+                o.z = pack_half2(v[j + 4] + b1.x, v[j + 5] + b1.y);
+                o.w = pack_half2(v[j + 6] + b1.z, v[j + 7] + b1.w);
+                *reinterpret_cast<uint4*>(dst + j) = o;
+            }
+        }
+        tc_fence_before_sync();
+        pend = false;
+    };
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
@@ -185,6 +290,11 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
         const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
         if (stack != loaded_stack) {                   // block-uniform: first item or Var-IO switch
+            if (pend) {                                // the pending MLP still reads the resident weights
+                mlp_hidden();
+                mlp_wait2();
+                mlp_store();
+            }
             __syncthreads();
             if (tid == 0) {
                 mbar_arrive_expect_tx(&bar_w, L::kBlob);
@@ -194,6 +304,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             ph_w ^= 1;
             loaded_stack = stack;
         }
+        // message source plane: the aggregated tensor of this user, or (two-user fast path) the
+        // other user's sp tensor gated by that user's activity flag
+        const int bu_a = p.pair_agg ? (bu ^ 1) : bu;
+        const bool a_live = !p.pair_agg || p.active_tx[bu_a] != 0.f;
         {   // carries of the hidden layers start as zeros (run-in rows; also the f < 0 padding)
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int i = tid; i < kCarryRows * kHRow / 16; i += kStackThreads) {
@@ -209,14 +323,16 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             const int nrow = max(fhi - flo, 0) * kT;
             if (tid == 0) {
                 const size_t grow = (size_t(bu) * p.F + flo) * kT;
+                const size_t grow_a = (size_t(bu_a) * p.F + flo) * kT;
                 const int so = (flo - zf0) * kT * L::kZRow;
                 if constexpr (MODE == kStackInit) {
                     mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * 64u);
                     if (nrow) bulk_g2s(sZ + so, reinterpret_cast<const uint8_t*>(p.z0) + grow * 64, uint32_t(nrow) * 64u, &bar_z);
                 } else {
-                    mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * 256u);
+                    mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * (a_live ? 256u : 128u));
                     if (nrow) {
-                        bulk_g2s(sZ + so, reinterpret_cast<const uint8_t*>(p.a_in) + grow * 128, uint32_t(nrow) * 128u, &bar_z);
+                        if (a_live)
+                            bulk_g2s(sZ + so, reinterpret_cast<const uint8_t*>(p.a_in) + grow_a * 128, uint32_t(nrow) * 128u, &bar_z);
                         bulk_g2s(sZ + L::kZArr + so, reinterpret_cast<const uint8_t*>(p.s_in) + grow * 128, uint32_t(nrow) * 128u, &bar_z);
                     }
                 }
@@ -232,6 +348,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                 }
             }
         };
+        if constexpr (MODE == kStackUpdate) {
+            if (!a_live)       // the only other user is inactive: its message is masked to zero (:192-193)
+                for (int i = tid; i < L::kZArr / 16; i += kStackThreads) st_shared_v4(sZ + i * 16, make_uint4(0, 0, 0, 0));
+        }
 
         // bias + ReLU epilogue of a hidden layer: TMEM -> fp16 rows of the fresh hidden tile;
         // rows whose subcarrier is outside the grid become zeros (padding of the next layer)
@@ -239,27 +359,37 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             const int f = f_out0 + efl;
             const bool in_grid = f >= 0 && f < p.F;
             const bool warp_oob = !__all_sync(0xffffffffu, in_grid || erow >= kTileRows);   // grid edges only
+            // both 32-column TMEM loads in flight, bias rows fetched while they complete
+            // (splitting the GEMM into two N=64 halves to overlap the second half with the first
+            // half's conversion was measured slower: 3.89 vs 3.60 ms per 30-slot step)
+            float v[2][32];
+            tmem_ld32(tmem_addr(tbase, q4 * 32, hc * 64), v[0]);
+            tmem_ld32(tmem_addr(tbase, q4 * 32, hc * 64 + 32), v[1]);
+            float4 bq[2][8];
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                float v[32];
-                const int col = hc * 64 + c0;
-                tmem_ld32(tmem_addr(tbase, q4 * 32, col), v);
-                tmem_ld_wait();
-                if (erow < kTileRows) {
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bq[c][j] = *reinterpret_cast<const float4*>(bias + hc * 64 + c * 32 + j * 4);
+            tmem_ld_wait();
+            if (erow < kTileRows) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = hc * 64 + c * 32;
+                    uint4 o[4];
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias + col + j);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias + col + j + 4);
-                        uint4 o;
-                        o.x = pack_relu_half2(v[j] + b0.x, v[j + 1] + b0.y);
-                        o.y = pack_relu_half2(v[j + 2] + b0.z, v[j + 3] + b0.w);
-                        o.z = pack_relu_half2(v[j + 4] + b1.x, v[j + 5] + b1.y);
-                        o.w = pack_relu_half2(v[j + 6] + b1.z, v[j + 7] + b1.w);
-                        if (warp_oob) {
-                            if (!in_grid) o = make_uint4(0, 0, 0, 0);
-                        }
-                        st_shared_v4(sH + erow * kHRow + (col + j) * 2, o);
+                        const float4 b0 = bq[c][j >> 2], b1 = bq[c][(j >> 2) + 1];
+                        o[j >> 3].x = pack_relu_half2(v[c][j] + b0.x, v[c][j + 1] + b0.y);
+                        o[j >> 3].y = pack_relu_half2(v[c][j + 2] + b0.z, v[c][j + 3] + b0.w);
+                        o[j >> 3].z = pack_relu_half2(v[c][j + 4] + b1.x, v[c][j + 5] + b1.y);
+                        o[j >> 3].w = pack_relu_half2(v[c][j + 6] + b1.z, v[c][j + 7] + b1.w);
                     }
+                    if (warp_oob && !in_grid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o[j] = make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_shared_v4(sH + erow * kHRow + (col + j * 8) * 2, o[j]);
                 }
             }
         };
@@ -303,9 +433,11 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
         stage_z(c0 - kRunIn + 1);
         for (int k = 0; k < nsteps; ++k) {
             const int b = c0 - kRunIn + kStepF * k;
+            NRX_TICK(21);                               // item set-up / loop overhead
             mbar_wait(&bar_z, ph_z);
             ph_z ^= 1;
             __syncthreads();                            // zero-filled rows / carries visible
+            NRX_TICK(0);
 
             // ================= layer 1: Z[b+1, b+12) -> H1[b+2, b+11) =================
             if constexpr (MODE == kStackInit) {
@@ -325,33 +457,50 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                                           sA + (qh >> 4) * 16384 + (qh & 1) * 8, (qh >> 1) & 7, 0, tail);
                 }
             }
+            NRX_TICK(1);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();                            // A complete; Z window free
+            NRX_TICK(2);
             issue_mma(L::oPw1, 128 * 128, L::KP1, 128);
             if (k + 1 < nsteps) stage_z(b + kStepF + 1);   // prefetch overlaps layers 1-3 of this step
+            if (pend) mlp_hidden();                     // previous tile's MLP, inside this GEMM's shadow
+            NRX_TICK(3);
             wait_mma();
+            if (pend) mlp_wait2();                      // its slabs sit where the hidden tile is about to land
+            NRX_TICK(4);
             epi_hidden(sBias, b + 2);
+            NRX_TICK(5);
             tc_fence_before_sync();
             __syncthreads();                            // H1 fresh tile complete, TMEM drained
+            NRX_TICK(6);
 
             // ================= layer 2: H1[b, b+11) -> H2[b+1, b+10) =================
             dw_hidden(sC1, L::oTap2);
+            NRX_TICK(7);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();                            // A complete; H1 tile + carry fully consumed
+            NRX_TICK(8);
             issue_mma(L::oPw2, 128 * 128, 128, 128);
             save_carry(sC1);
+            if (pend) mlp_store();
+            NRX_TICK(9);
             wait_mma();
+            NRX_TICK(10);
             epi_hidden(sBias + 128, b + 1);
+            NRX_TICK(11);
             tc_fence_before_sync();
             __syncthreads();
+            NRX_TICK(12);
 
             // ================= layer 3: H2[b-1, b+10) -> out[b, b+9) =================
             dw_hidden(sC2, L::oTap3);
+            NRX_TICK(13);
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
+            NRX_TICK(14);
             issue_mma(L::oPw3, 64 * 128, 128, 64);
             save_carry(sC2);
             // prefetch what the copy-out needs from global memory while the GEMM runs:
@@ -375,17 +524,22 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                     }
                 }
             }
+            NRX_TICK(15);
             wait_mma();
+            NRX_TICK(16);
             {   // fp32 staging [128][64] in the A buffer (free now): 16 chunks of 4 floats, chunk ^ (row & 7)
                 float v[32];
                 const int col = hc * 32;
                 tmem_ld32(tmem_addr(tbase, q4 * 32, col), v);
-                tmem_ld_wait();
                 const float* b3 = sBias + 256;
+                float4 b3q[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b3q[j] = *reinterpret_cast<const float4*>(b3 + col + j * 4);
+                tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int c4 = (col + j) >> 2;
-                    const float4 bb = *reinterpret_cast<const float4*>(b3 + col + j);
+                    const float4 bb = b3q[j >> 2];
                     float4 o;
                     o.x = v[j] + bb.x;
                     o.y = v[j + 1] + bb.y;
@@ -394,8 +548,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                     *reinterpret_cast<float4*>(sA + erow * 256 + ((c4 ^ (erow & 7)) << 4)) = o;
                 }
             }
+            NRX_TICK(17);
             tc_fence_before_sync();
             __syncthreads();                            // staging complete; TMEM drained
+            NRX_TICK(18);
 
             // ---- coalesced copy-out of the chunk's own rows: residual (update) / pe append (init) ----
 #pragma unroll
@@ -429,13 +585,43 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                 pk.w = pack_half2(a[6], a[7]);
                 const size_t grow = (size_t(bu) * p.F + (b + co_fl[it])) * kT + co_t[it];
                 *reinterpret_cast<uint4*>(p.s_out + grow * 64 + co_g * 8) = pk;
+                if (p.sp_out) st_shared_v4(sH + rr * 128 + ((co_g ^ (rr & 7)) << 4), pk);   // A slab of the message MLP
             }
-            __syncthreads();                            // staging free before the next depthwise pass
+            NRX_TICK(19);
+            if (p.sp_out) {
+                // ---- message MLP of the next AggregateUserStates on the fresh state tile (:184-188),
+                //      sp = Dense2(relu(Dense1(s_new))): the first GEMM is issued here, the rest of the
+                //      chain (mlp_hidden / mlp_store) runs inside the MMA bubbles of the next step
+                fence_proxy_async_smem();
+                tc_fence_before_sync();
+                __syncthreads();                        // state slab complete; fp32 staging free
+                if (tid == 0) {
+                    tc_fence_after_sync();
+                    umma_gemm_k(tbase + 128, smem_u32(sH), 16384, smem_u32(sW + L::oAggW1), 8192, 64,
+                                umma_idesc_f16(128, 64), false);
+                    umma_commit(&bar_mlp);
+                }
+                pend = true;
+                pend_row0 = (size_t(bu) * p.F + b) * kT;     // global row of tile row 0
+                pend_lo = (c0 - b) * kT;                     // tile rows [pend_lo, pend_hi) belong to the chunk
+                pend_hi = (c1 - b) * kT;
+            } else
+            __syncthreads();                            // staging / slabs free before the next depthwise pass
+            NRX_TICK(20);
         }
     }
+    if (pend) {                                         // flush the last tile's MLP
+        mlp_hidden();
+        mlp_wait2();
+        mlp_store();
+    }
+#ifdef NRX_PHASE_TIMING
+    if (blockIdx.x == 0 && tid == 32)
+        for (int i = 0; i < 32; ++i) g_phase_cycles[i] += s_phase[i];
+#endif
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 128);
+    if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
 // Number of chunks per (slot, user) plane that minimises the makespan  waves x steps-per-item  on

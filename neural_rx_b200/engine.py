@@ -184,9 +184,10 @@ class NrxEngine:
         self._check(self._lib.nrx_set_slots_per_pass(self._h, int(slots)))
         self._ws = None
 
-    def set_fused(self, fused: bool) -> None:
-        """Fused stack kernels (default) or one kernel per SeparableConv2D layer (cross-check)."""
-        self._check(self._lib.nrx_set_fused(self._h, int(bool(fused))))
+    def set_fused(self, fused) -> None:
+        """1/True: fused stack kernels + aggregation kernel (default); 2: fused stacks with the
+        message MLP in their tail (two users); 0/False: one kernel per SeparableConv2D layer."""
+        self._check(self._lib.nrx_set_fused(self._h, int(fused)))
 
     def set_host_chunk(self, slots: int) -> None:
         """Slots per pipeline chunk of the host-buffer call (0 = default)."""

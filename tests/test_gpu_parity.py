@@ -99,16 +99,20 @@ def test_fused_equals_layerwise(label, n_prb, batch):
     if cfg.num_mcss_supported > 1:
         kw = dict(io_index=np.tile(np.array([[0, 1]], np.int32), (batch, 1)))
     outs = []
-    for fused in (True, False):
+    for fused in (1, 2, 0):
         eng = _engine(cfg, weights, grid, fused=fused)
         outs.append(_run(eng, sb, **dict(kw)))
         eng.close()
     for k in ("llr", "llr_grid", "h_hat_refined"):
-        assert rel_l2(outs[0][k], outs[1][k]) <= 1e-6, k
+        assert rel_l2(outs[0][k], outs[2][k]) <= 1e-6, k
+        # the two-user fast path takes the other user's message directly instead of forming
+        # (sp_0 + sp_1) - sp_u in fp32 (utils/neural_rx.py:196) and rounds sp (not a) to fp16:
+        # same function, differences at fp16 round-off level
+        assert rel_l2(outs[1][k], outs[2][k]) <= 2e-3, k
     arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
     if cfg.num_mcss_supported == 1:
         ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx)
-        assert rel_l2(outs[1]["llr"], ref["llr"]) <= TOL_EXACT
+        assert rel_l2(outs[2]["llr"], ref["llr"]) <= TOL_EXACT
 
 
 def test_random_weights_parity():
