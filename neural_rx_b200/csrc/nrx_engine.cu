@@ -502,8 +502,10 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_agg_kernel<3>, agg_smem_bytes(3)));
     acc(set_smem(nrx_agg_kernel<4>, agg_smem_bytes(4)));
     acc(set_smem(nrx_readout_kernel, kRoSmem));
-    acc(set_smem(nrx_stack_kernel<kStackInit>, StackSmem<kStackInit>::kTotal));
-    acc(set_smem(nrx_stack_kernel<kStackUpdate>, StackSmem<kStackUpdate>::kTotal));
+    acc(set_smem(nrx_stack_kernel<kStackInit, false>, StackSmem<kStackInit>::kTotal));
+    acc(set_smem(nrx_stack_kernel<kStackUpdate, false>, StackSmem<kStackUpdate>::kTotal));
+    acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
+    acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
     NRX_CUDA(cudaDeviceSynchronize());
     *out = e;
@@ -650,7 +652,8 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             kp.sp_out = pair ? sp_cur : nullptr;
             {
                 Timed t(e, st, NRX_K_STACK_INIT);
-                nrx_stack_kernel<kStackInit><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+                if (pair) nrx_stack_kernel<kStackInit, true><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+                else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
             kp.stack_index = nullptr;
             kp.default_stack = 0;
@@ -663,7 +666,8 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
                 kp.wblob = e->stack_upd_blobs[it];
                 {
                     Timed t(e, st, NRX_K_STACK_UPD);
-                    nrx_stack_kernel<kStackUpdate><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+                    if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+                    else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                 }
                 __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
                 tmp = sp_cur; sp_cur = sp_alt; sp_alt = tmp;

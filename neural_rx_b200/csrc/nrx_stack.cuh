@@ -20,6 +20,8 @@
 // Shared memory (update stack): weights of all three layers 88 KB | A operand 32 KB |
 // hidden tile 9 sc + two 2-sc carries 48 KB | Z window (a | s) 38.5 KB  = 207 KB, one CTA per SM.
 #pragma once
+#include <type_traits>
+
 #include "nrx_kernels.cuh"
 
 namespace nrx {
@@ -150,7 +152,7 @@ __device__ unsigned long long g_phase_cycles[32];
 #define NRX_TICK(i) do { } while (0)
 #endif
 
-template <int MODE>
+template <int MODE, bool MLP>
 __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams p) {
     using L = StackSmem<MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);   // [0,128) layer accumulator, [128,192) / [192,256) message MLP
+    if (warp == 0) tmem_alloc(&tmem_slot, MLP ? 256 : 128);   // [0,128) layer accumulator, [128,192) / [192,256) message MLP
     if (tid == 0) {
         mbar_init(&bar_z, 1);
         mbar_init(&bar_w, 1);
@@ -284,13 +286,14 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
         pend = false;
     };
 
+    bool z_prefetched = false;                          // the next item's first window is already in flight
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
         const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
         if (stack != loaded_stack) {                   // block-uniform: first item or Var-IO switch
-            if (pend) {                                // the pending MLP still reads the resident weights
+            if (MLP && pend) {                         // the pending MLP still reads the resident weights
                 mlp_hidden();
                 mlp_wait2();
                 mlp_store();
@@ -318,20 +321,20 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 
         // fetch the 11-subcarrier layer-1 window starting at subcarrier zf0 (thread 0) and zero the
         // rows outside the grid (all threads); the window buffer must be free when this is called
-        auto stage_z = [&](int zf0) {
+        auto stage_z_of = [&](int zbu, int zbu_a, bool za_live, int zf0) {
             const int flo = max(zf0, 0), fhi = min(zf0 + kStepF + 2, p.F);
             const int nrow = max(fhi - flo, 0) * kT;
             if (tid == 0) {
-                const size_t grow = (size_t(bu) * p.F + flo) * kT;
-                const size_t grow_a = (size_t(bu_a) * p.F + flo) * kT;
+                const size_t grow = (size_t(zbu) * p.F + flo) * kT;
+                const size_t grow_a = (size_t(zbu_a) * p.F + flo) * kT;
                 const int so = (flo - zf0) * kT * L::kZRow;
                 if constexpr (MODE == kStackInit) {
                     mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * 64u);
                     if (nrow) bulk_g2s(sZ + so, reinterpret_cast<const uint8_t*>(p.z0) + grow * 64, uint32_t(nrow) * 64u, &bar_z);
                 } else {
-                    mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * (a_live ? 256u : 128u));
+                    mbar_arrive_expect_tx(&bar_z, uint32_t(nrow) * (za_live ? 256u : 128u));
                     if (nrow) {
-                        if (a_live)
+                        if (za_live)
                             bulk_g2s(sZ + so, reinterpret_cast<const uint8_t*>(p.a_in) + grow_a * 128, uint32_t(nrow) * 128u, &bar_z);
                         bulk_g2s(sZ + L::kZArr + so, reinterpret_cast<const uint8_t*>(p.s_in) + grow * 128, uint32_t(nrow) * 128u, &bar_z);
                     }
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                 }
             }
         };
+        auto stage_z = [&](int zf0) { stage_z_of(bu, bu_a, a_live, zf0); };
         if constexpr (MODE == kStackUpdate) {
             if (!a_live)       // the only other user is inactive: its message is masked to zero (:192-193)
                 for (int i = tid; i < L::kZArr / 16; i += kStackThreads) st_shared_v4(sZ + i * 16, make_uint4(0, 0, 0, 0));
@@ -400,21 +404,39 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 #pragma unroll
             for (int i = 0; i < 9; ++i) kk[i] = lds64(sW + tap_off + (i * kp + q * 4) * 2);
         };
-        auto dw_hidden = [&](const uint8_t* carry, int tap_off) {
-            if (act_h) {
-                uint2 kk[9];
-                load_taps(kk, tap_off, 128, qh);
-                dw_slide<kHRow, kStepF>(carry + qh * 8, sH + qh * 8, 2 * ph, ph > 0, ph < 6, kk,
-                                        sA + (qh >> 4) * 16384 + (qh & 1) * 8, (qh >> 1) & 7, 0, tail);
+        // One 128-channel depthwise pass, balanced over the four SM sub-partitions: warps 0-6 own one
+        // symbol pair each and slide over output subcarriers 0..7; warp 7 computes subcarrier 8 for all
+        // seven symbol pairs (it is the only one that sees the last two input subcarriers, so it also
+        // keeps the next carry).  Busiest sub-partition: 576 HFMA2 instead of 648.
+        uint2 tail7[7][2][2];
+        auto dw128 = [&](auto rs_tag, const uint8_t* carry, const uint8_t* fresh, int tap_off) {
+            constexpr int RS = decltype(rs_tag)::value;
+            uint2 kk[9];
+            load_taps(kk, tap_off, 128, qh);
+            uint8_t* a_thr = sA + (qh >> 4) * 16384 + (qh & 1) * 8;
+            if (warp < 7) {
+                uint2 unused[2][2];
+                dw_slide<RS, kStepF - 1>(carry, fresh, 2 * ph, ph > 0, ph < 6, kk, a_thr, (qh >> 1) & 7, 0, unused);
+            } else {
+                const uint8_t* c8 = fresh + (kStepF - 3) * (kT * RS);      // input subcarriers 8, 9, 10
+#pragma unroll
+                for (int pp = 0; pp < 7; ++pp)
+                    dw_slide<RS, 1>(c8, c8 + 2 * (kT * RS), 2 * pp, pp > 0, pp < 6, kk, a_thr, (qh >> 1) & 7,
+                                    (kStepF - 1) * kT, tail7[pp]);
             }
         };
+        auto dw_hidden = [&](const uint8_t* carry, int tap_off) {
+            dw128(std::integral_constant<int, kHRow>{}, carry + qh * 8, sH + qh * 8, tap_off);
+        };
         auto save_carry = [&](uint8_t* carry) {         // after the post-depthwise barrier
-            if (act_h) {
+            if (warp == 7) {
 #pragma unroll
-                for (int ci = 0; ci < 2; ++ci)
+                for (int pp = 0; pp < 7; ++pp)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        sts64(carry + ((ci * kT) + 2 * ph + e) * kHRow + qh * 8, tail[ci][e]);
+                    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            sts64(carry + ((ci * kT) + 2 * pp + e) * kHRow + qh * 8, tail7[pp][ci][e]);
             }
         };
         auto issue_mma = [&](int w_off, int b_slab_bytes, int K, int N) {
@@ -430,7 +452,8 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             tc_fence_after_sync();
         };
 
-        stage_z(c0 - kRunIn + 1);
+        if (!z_prefetched) stage_z(c0 - kRunIn + 1);
+        z_prefetched = false;
         for (int k = 0; k < nsteps; ++k) {
             const int b = c0 - kRunIn + kStepF * k;
             NRX_TICK(21);                               // item set-up / loop overhead
@@ -449,13 +472,8 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                                     seg1 * 3 * kT, tail);
                 }
             } else {
-                if (act_h) {
-                    uint2 kk[9];
-                    load_taps(kk, L::oTap1, 128, qh);
-                    const uint8_t* zc = sZ + (qh >> 4) * L::kZArr + (qh & 15) * 8;
-                    dw_slide<128, kStepF>(zc, zc + 2 * kT * 128, 2 * ph, ph > 0, ph < 6, kk,
-                                          sA + (qh >> 4) * 16384 + (qh & 1) * 8, (qh >> 1) & 7, 0, tail);
-                }
+                const uint8_t* zc = sZ + (qh >> 4) * L::kZArr + (qh & 15) * 8;
+                dw128(std::integral_constant<int, 128>{}, zc, zc + 2 * kT * 128, L::oTap1);
             }
             NRX_TICK(1);
             fence_proxy_async_smem();
@@ -463,11 +481,23 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             __syncthreads();                            // A complete; Z window free
             NRX_TICK(2);
             issue_mma(L::oPw1, 128 * 128, L::KP1, 128);
-            if (k + 1 < nsteps) stage_z(b + kStepF + 1);   // prefetch overlaps layers 1-3 of this step
-            if (pend) mlp_hidden();                     // previous tile's MLP, inside this GEMM's shadow
+            if (k + 1 < nsteps) {
+                stage_z(b + kStepF + 1);                // prefetch overlaps layers 1-3 of this step
+            } else if (item + int(gridDim.x) < p.num_items) {   // last step: first window of the CTA's next item
+                const int nitem = item + int(gridDim.x);
+                const int nbu = nitem / p.n_chunks, ncj = nitem - nbu * p.n_chunks;
+                const int nstack = p.stack_index ? p.stack_index[nbu] : p.default_stack;
+                if (nstack == loaded_stack) {
+                    const int nbu_a = p.pair_agg ? (nbu ^ 1) : nbu;
+                    const bool na_live = !p.pair_agg || p.active_tx[nbu_a] != 0.f;
+                    stage_z_of(nbu, nbu_a, na_live, int((long long)ncj * p.F / p.n_chunks) - kRunIn + 1);
+                    z_prefetched = true;
+                }
+            }
+            if (MLP && pend) mlp_hidden();              // previous tile's MLP, inside this GEMM's shadow
             NRX_TICK(3);
             wait_mma();
-            if (pend) mlp_wait2();                      // its slabs sit where the hidden tile is about to land
+            if (MLP && pend) mlp_wait2();               // its slabs sit where the hidden tile is about to land
             NRX_TICK(4);
             epi_hidden(sBias, b + 2);
             NRX_TICK(5);
@@ -484,26 +514,8 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             NRX_TICK(8);
             issue_mma(L::oPw2, 128 * 128, 128, 128);
             save_carry(sC1);
-            if (pend) mlp_store();
-            NRX_TICK(9);
-            wait_mma();
-            NRX_TICK(10);
-            epi_hidden(sBias + 128, b + 1);
-            NRX_TICK(11);
-            tc_fence_before_sync();
-            __syncthreads();
-            NRX_TICK(12);
-
-            // ================= layer 3: H2[b-1, b+10) -> out[b, b+9) =================
-            dw_hidden(sC2, L::oTap3);
-            NRX_TICK(13);
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            NRX_TICK(14);
-            issue_mma(L::oPw3, 64 * 128, 128, 64);
-            save_carry(sC2);
-            // prefetch what the copy-out needs from global memory while the GEMM runs:
+            if (MLP && pend) mlp_store();
+            // prefetch what the copy-out needs from global memory (issued two GEMMs ahead of its use):
             // the old state (residual, update stack) or the positional encoding (StateInit)
             const int u = bu % p.U;
             uint4 co_old[4];
@@ -524,6 +536,24 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                     }
                 }
             }
+            NRX_TICK(9);
+            wait_mma();
+            NRX_TICK(10);
+            epi_hidden(sBias + 128, b + 1);
+            NRX_TICK(11);
+            tc_fence_before_sync();
+            __syncthreads();
+            NRX_TICK(12);
+
+            // ================= layer 3: H2[b-1, b+10) -> out[b, b+9) =================
+            dw_hidden(sC2, L::oTap3);
+            NRX_TICK(13);
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            NRX_TICK(14);
+            issue_mma(L::oPw3, 64 * 128, 128, 64);
+            save_carry(sC2);
             NRX_TICK(15);
             wait_mma();
             NRX_TICK(16);
@@ -585,10 +615,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                 pk.w = pack_half2(a[6], a[7]);
                 const size_t grow = (size_t(bu) * p.F + (b + co_fl[it])) * kT + co_t[it];
                 *reinterpret_cast<uint4*>(p.s_out + grow * 64 + co_g * 8) = pk;
-                if (p.sp_out) st_shared_v4(sH + rr * 128 + ((co_g ^ (rr & 7)) << 4), pk);   // A slab of the message MLP
+                if (MLP && p.sp_out) st_shared_v4(sH + rr * 128 + ((co_g ^ (rr & 7)) << 4), pk);   // A slab of the message MLP
             }
             NRX_TICK(19);
-            if (p.sp_out) {
+            if (MLP && p.sp_out) {
                 // ---- message MLP of the next AggregateUserStates on the fresh state tile (:184-188),
                 //      sp = Dense2(relu(Dense1(s_new))): the first GEMM is issued here, the rest of the
                 //      chain (mlp_hidden / mlp_store) runs inside the MMA bubbles of the next step
@@ -610,7 +640,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             NRX_TICK(20);
         }
     }
-    if (pend) {                                         // flush the last tile's MLP
+    if (MLP && pend) {                                  // flush the last tile's MLP
         mlp_hidden();
         mlp_wait2();
         mlp_store();
@@ -621,7 +651,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 #endif
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    if (warp == 0) tmem_dealloc(tbase, MLP ? 256 : 128);
 }
 
 // Number of chunks per (slot, user) plane that minimises the makespan  waves x steps-per-item  on
