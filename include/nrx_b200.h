@@ -116,6 +116,28 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y,
                 int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
                 float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes);
 
+/* Replaces: NeuralReceiverONNX.forward (utils/neural_rx.py:1773-1812) with NRPreprocessing
+ * (:1614-1713) — the Aerial / TensorRT-shaped call whose seven inputs are the TRT bindings of
+ * scripts/export_onnx.py:153-160.  nrx_set_aerial_dmrs takes the two integer inputs
+ *   dmrs_ofdm_pos       [U][n_sym] int32 (host)  DMRS symbol indices per UE
+ *   dmrs_subcarrier_pos [U][n_sc]  int32 (host)  non-zero pilot subcarriers inside one PRB per UE
+ * and precomputes the per-PRB nearest-pilot table and positional encoding (they only change
+ * with the DMRS configuration).  nrx_forward_aerial takes DEVICE pointers:
+ *   rx_slot_real / rx_slot_imag  [B][F][T][N_rx] float32
+ *   h_hat_real / h_hat_imag      [B][n_pilots][U][N_rx] float32  LS estimates at the non-zero
+ *                                pilots, DMRS-symbol major (n_pilots = n_sym * F/12 * n_sc)
+ *   active_dmrs_ports            [B][U] float32 0/1
+ * outputs
+ *   llr    [B][bits][U][F][T] float32 = MINUS the Sionna-convention LLR (:1809-1810)
+ *   h_hat  [B][U][F][T][2*N_rx] float32 refined channel estimate.
+ * Single-MCS models only (the reference: "no support for mixed MCS", :1796). */
+int nrx_set_aerial_dmrs(nrx_engine* e, const int32_t* dmrs_ofdm_pos, int32_t n_sym,
+                        const int32_t* dmrs_subcarrier_pos, int32_t n_sc);
+int nrx_forward_aerial(nrx_engine* e, void* cuda_stream, int32_t batch, const float* rx_slot_real,
+                       const float* rx_slot_imag, const float* h_hat_real, const float* h_hat_imag,
+                       const float* active_dmrs_ports, float* llr, float* h_hat, void* workspace,
+                       size_t workspace_bytes);
+
 /* Same call with HOST buffers — the call a drop-in user of the reference's receiver makes with
  * NumPy arrays.  The batch flows through a 3-stage pipeline in chunks of nrx_set_host_chunk slots
  * (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 overlap on three streams).  Pinned /

@@ -78,6 +78,10 @@ struct nrx_engine {
     float* pos_enc = nullptr;
     int32_t* data_index = nullptr;
     int n_pilot_slots = 0;
+    // Aerial / TensorRT-shaped entry point (nrx_set_aerial_dmrs)
+    int32_t* nn_prb = nullptr;                      // [U][F*T] ordinal of the nearest non-zero pilot (per-PRB rule)
+    float* pos_enc_aerial = nullptr;                // [U][F][T][2]
+    int aerial_pilots = 0;                          // non-zero pilots per user
     int64_t mac_fixed[NRX_MAX_IO] = {0};            // StateInit + readouts per head
     int64_t mac_per_it = 0;
     // per-kernel event timing (nrx_set_profiling)
@@ -279,6 +283,8 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->focc);
     cudaFree(e->pos_enc);
     cudaFree(e->data_index);
+    cudaFree(e->nn_prb);
+    cudaFree(e->pos_enc_aerial);
     cudaFree(e->d_io);
     cudaFree(e->d_ws);
     if (e->h_pin) cudaFreeHost(e->h_pin);
@@ -581,10 +587,19 @@ int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs) {
     return NRX_OK;
 }
 
-int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, const float* active_tx,
-                const int32_t* io_index, const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr,
-                float* llr_grid, float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes) {
-    if (!e || !y || !active_tx || !workspace) return fail(NRX_ERR_INVALID, "nrx_forward: null argument");
+}  // extern "C"
+
+namespace {
+
+struct AerialIn {             // inputs of the Aerial-shaped call (null for the Sionna-shaped one)
+    const float *y_re, *y_im, *h_re, *h_im;
+};
+
+int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn* aer, const void* y, const float* active_tx,
+                 const int32_t* io_index, const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr,
+                 float* llr_grid, float* llr_aerial, float* h_hat_refined, float* h_hat_ls, void* workspace,
+                 size_t workspace_bytes) {
+    if (!e || (!y && !aer) || !active_tx || !workspace) return fail(NRX_ERR_INVALID, "nrx_forward: null argument");
     if (batch < 1) return fail(NRX_ERR_INVALID, "batch must be >= 1");
     const nrx_model_desc& d = e->d;
     if (llr_head < 0 || llr_head >= d.n_io) return fail(NRX_ERR_INVALID, "llr_head out of range");
@@ -605,9 +620,11 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
 
     const int F = d.num_subcarriers, U = d.max_num_tx, N = d.num_rx_ant;
     const int per_slot = F * kT;
+    const float* pe_tab = aer ? e->pos_enc_aerial : e->pos_enc;
     {
         Timed t(e, st, NRX_K_POWER);
-        nrx_power_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(static_cast<const float2*>(y), partial, N * per_slot);
+        if (aer) nrx_power_planar_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(aer->y_re, aer->y_im, partial, N * per_slot);
+        else nrx_power_kernel<<<dim3(kPowerParts, batch), 256, 0, st>>>(static_cast<const float2*>(y), partial, N * per_slot);
     }
 
     const int bp_max = pass_slots(e, batch);
@@ -623,7 +640,14 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
         pp.z0 = z0;
         pp.h_ls = h_hat_ls;
         pp.F = F; pp.U = U; pp.N = N; pp.n_pilot_slots = e->n_pilot_slots; pp.b0 = b0; pp.bp = bp;
-        {
+        if (aer) {
+            PrepAerialParams pa{};
+            pa.y_re = aer->y_re; pa.y_im = aer->y_im; pa.h_re = aer->h_re; pa.h_im = aer->h_im;
+            pa.partial = partial; pa.nn_prb = e->nn_prb; pa.pos_enc = pe_tab; pa.z0 = z0;
+            pa.F = F; pa.U = U; pa.N = N; pa.n_pilots = e->aerial_pilots; pa.b0 = b0; pa.bp = bp;
+            Timed t(e, st, NRX_K_PREP);
+            nrx_prep_aerial_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
+        } else {
             Timed t(e, st, NRX_K_PREP);
             nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
         }
@@ -636,7 +660,7 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             kp.F = F; kp.U = U; kp.d_s = d.d_s;
             kp.n_chunks = choose_chunks(BU, F, e->num_sms);
             kp.num_items = kp.n_chunks * BU;
-            kp.pos_enc = e->pos_enc;
+            kp.pos_enc = pe_tab;
             const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
             // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
             // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
@@ -677,7 +701,7 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
             sp.F = F; sp.U = U; sp.d_s = d.d_s;
             sp.tiles_per_bu = (F + kTileF - 1) / kTileF;
             sp.num_tiles = sp.tiles_per_bu * BU;
-            sp.pos_enc = e->pos_enc;
+            sp.pos_enc = pe_tab;
             // ---- StateInit (:107-132), stack per user = one-hot mcs_ue_mask (:562-569) -------------
             sp.stack_index = io_index ? io_index + size_t(b0) * U : nullptr;
             sp.default_stack = llr_head;
@@ -717,6 +741,7 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
         rp.llr = llr ? llr + bu0 * d.num_data_res * out_bits : nullptr;
         rp.llr_grid = llr_grid ? llr_grid + bu0 * per_slot * out_bits : nullptr;
         rp.h_ref = h_hat_refined ? h_hat_refined + bu0 * per_slot * 2 * N : nullptr;
+        rp.llr_aerial = llr_aerial ? llr_aerial + bu0 * per_slot * out_bits : nullptr;
         rp.F = F; rp.U = U; rp.N2 = 2 * N; rp.out_bits = out_bits; rp.n_data = d.num_data_res;
         rp.rows_per_bu = per_slot;
         rp.tiles_per_bu = (per_slot + 127) / 128;
@@ -730,6 +755,93 @@ int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, 
     }
     NRX_CUDA(cudaGetLastError());
     return NRX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nrx_forward(nrx_engine* e, void* cuda_stream, int32_t batch, const void* y, const float* active_tx,
+                const int32_t* io_index, const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr,
+                float* llr_grid, float* h_hat_refined, float* h_hat_ls, void* workspace, size_t workspace_bytes) {
+    if (!y) return fail(NRX_ERR_INVALID, "nrx_forward: null argument");
+    return forward_impl(e, cuda_stream, batch, nullptr, y, active_tx, io_index, head_index, llr_head, out_bits, llr, llr_grid,
+                        nullptr, h_hat_refined, h_hat_ls, workspace, workspace_bytes);
+}
+
+// NRPreprocessing._calculate_nn_indices (utils/neural_rx.py:1631-1670) on the 12 x T template of one
+// PRB, tiled over the PRBs: nearest non-zero pilot per RE (Manhattan distance, candidates enumerated
+// subcarrier-major / symbol-minor, first minimum wins) and the positional encoding of the template.
+int nrx_set_aerial_dmrs(nrx_engine* e, const int32_t* dmrs_ofdm_pos, int32_t n_sym, const int32_t* dmrs_subcarrier_pos,
+                        int32_t n_sc) {
+    if (!e || !dmrs_ofdm_pos || !dmrs_subcarrier_pos) return fail(NRX_ERR_INVALID, "nrx_set_aerial_dmrs: null argument");
+    const nrx_model_desc& d = e->d;
+    const int F = d.num_subcarriers, U = d.max_num_tx, T = kT;
+    if (F % 12) return fail(NRX_ERR_INVALID, "the Aerial entry point needs whole PRBs");
+    if (n_sym < 1 || n_sym > NRX_MAX_DMRS || n_sc < 2 || n_sc > 12 || n_sc % 2)
+        return fail(NRX_ERR_INVALID, "need 1..4 DMRS symbols and an even number (<= 12) of pilots per PRB");
+    if (d.n_io != 1) return fail(NRX_ERR_UNSUPPORTED, "NeuralReceiverONNX has no support for mixed MCS");
+    for (int i = 0; i < U * n_sym; ++i)
+        if (dmrs_ofdm_pos[i] < 0 || dmrs_ofdm_pos[i] >= T) return fail(NRX_ERR_INVALID, "dmrs_ofdm_pos out of range");
+    for (int i = 0; i < U * n_sc; ++i)
+        if (dmrs_subcarrier_pos[i] < 0 || dmrs_subcarrier_pos[i] >= 12)
+            return fail(NRX_ERR_INVALID, "dmrs_subcarrier_pos out of range");
+    const int n_prb = F / 12, per_sym = n_prb * n_sc, TF = T * F;
+    std::vector<int32_t> nn(size_t(U) * TF);
+    std::vector<float> pe(size_t(U) * TF * 2);
+    for (int u = 0; u < U; ++u) {
+        const int32_t* tp = dmrs_ofdm_pos + u * n_sym;
+        const int32_t* sp = dmrs_subcarrier_pos + u * n_sc;
+        double dist[2][12 * kT], mean[2] = {0, 0}, var[2] = {0, 0};
+        int best_k[12 * kT], best_j[12 * kT];
+        for (int sc = 0; sc < 12; ++sc)
+            for (int t = 0; t < T; ++t) {
+                int best = 1 << 30, bk = 0, bj = 0, dt_min = 1 << 30, df_min = 1 << 30;
+                for (int k = 0; k < n_sc; ++k)
+                    for (int j = 0; j < n_sym; ++j) {
+                        const int df = std::abs(sc - sp[k]), dt = std::abs(t - tp[j]);
+                        if (df + dt < best) { best = df + dt; bk = k; bj = j; }
+                        if (dt < dt_min) dt_min = dt;
+                        if (df < df_min) df_min = df;
+                    }
+                best_k[sc * T + t] = bk;
+                best_j[sc * T + t] = bj;
+                dist[0][sc * T + t] = dt_min;
+                dist[1][sc * T + t] = df_min;
+            }
+        for (int c = 0; c < 2; ++c) {
+            for (int i = 0; i < 12 * T; ++i) mean[c] += dist[c][i];
+            mean[c] /= 12 * T;
+            for (int i = 0; i < 12 * T; ++i) var[c] += (dist[c][i] - mean[c]) * (dist[c][i] - mean[c]);
+            var[c] = std::sqrt(var[c] / (12 * T)) + 1e-8;                      // population std + 1e-8 (:1655-1658)
+        }
+        for (int f = 0; f < F; ++f)
+            for (int t = 0; t < T; ++t) {
+                const int prb = f / 12, i = (f % 12) * T + t;
+                nn[size_t(u) * TF + f * T + t] = best_j[i] * per_sym + prb * n_sc + best_k[i];
+                for (int c = 0; c < 2; ++c)
+                    pe[(size_t(u) * TF + f * T + t) * 2 + c] = float((dist[c][i] - mean[c]) / var[c]);
+            }
+    }
+    NRX_CUDA(cudaSetDevice(e->device));
+    if (!e->nn_prb) NRX_CUDA(cudaMalloc(&e->nn_prb, nn.size() * 4));
+    if (!e->pos_enc_aerial) NRX_CUDA(cudaMalloc(&e->pos_enc_aerial, pe.size() * 4));
+    NRX_CUDA(cudaDeviceSynchronize());
+    NRX_CUDA(cudaMemcpy(e->nn_prb, nn.data(), nn.size() * 4, cudaMemcpyHostToDevice));
+    NRX_CUDA(cudaMemcpy(e->pos_enc_aerial, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+    e->aerial_pilots = n_sym * per_sym;
+    return NRX_OK;
+}
+
+int nrx_forward_aerial(nrx_engine* e, void* cuda_stream, int32_t batch, const float* rx_slot_real, const float* rx_slot_imag,
+                       const float* h_hat_real, const float* h_hat_imag, const float* active_dmrs_ports, float* llr,
+                       float* h_hat, void* workspace, size_t workspace_bytes) {
+    if (!e || !rx_slot_real || !rx_slot_imag || !h_hat_real || !h_hat_imag)
+        return fail(NRX_ERR_INVALID, "nrx_forward_aerial: null argument");
+    if (!e->nn_prb) return fail(NRX_ERR_INVALID, "nrx_forward_aerial: call nrx_set_aerial_dmrs first");
+    const AerialIn in{rx_slot_real, rx_slot_imag, h_hat_real, h_hat_imag};
+    return forward_impl(e, cuda_stream, batch, &in, nullptr, active_dmrs_ports, nullptr, nullptr, 0, e->d.io_bits[0], nullptr,
+                        nullptr, llr, h_hat, nullptr, workspace, workspace_bytes);
 }
 
 #ifdef NRX_PHASE_TIMING

@@ -158,6 +158,83 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
 }
 
 // =============================================================================================
+// 2b. Aerial / TensorRT-shaped pre-processing (NRPreprocessing, utils/neural_rx.py:1614-1713):
+//     rx_slot_{real,imag} [B][F][T][N], LS estimates at the non-zero pilots h_hat_{real,imag}
+//     [B][n_pilots][U][N] (DMRS-symbol major), FOCC removal = mean of adjacent pilot pairs,
+//     per-PRB nearest-pilot gather, normalisation, positional encoding -> the same z0 rows.
+// =============================================================================================
+__global__ void __launch_bounds__(256) nrx_power_planar_kernel(const float* __restrict__ re, const float* __restrict__ im,
+                                                               float* __restrict__ partial, int n_real) {
+    const int b = blockIdx.y, part = blockIdx.x;
+    const int per = (n_real + kPowerParts - 1) / kPowerParts;
+    const int lo = part * per, hi = min(lo + per, n_real);
+    const float* rb = re + size_t(b) * n_real;
+    const float* ib = im + size_t(b) * n_real;
+    float acc = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += 256) {
+        const float a = __ldg(rb + i), c = __ldg(ib + i);
+        acc = fmaf(a, a, acc);
+        acc = fmaf(c, c, acc);
+    }
+    __shared__ float red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[b * kPowerParts + part] = red[0];
+}
+
+struct PrepAerialParams {
+    const float* y_re;        // [B][F][T][N]
+    const float* y_im;
+    const float* h_re;        // [B][n_pilots][U][N]
+    const float* h_im;
+    const float* partial;     // [B][kPowerParts]
+    const int32_t* nn_prb;    // [U][F*T]  pilot ordinal per RE, (f, t) order
+    const float* pos_enc;     // [U][F][T][2]
+    __half* z0;               // [Bp*U*F*T][32]
+    int F, U, N, n_pilots, b0, bp;
+};
+
+__global__ void __launch_bounds__(256) nrx_prep_aerial_kernel(PrepAerialParams p) {
+    const int per_slot = p.F * kT;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= p.bp * per_slot) return;
+    const int bl = idx / per_slot, rem = idx - bl * per_slot;    // rem = f * T + t
+    const int b = p.b0 + bl;
+    const int N = p.N;
+    const float g = slot_gain(p.partial, b, 2 * N * per_slot);
+    const float* yr = p.y_re + (size_t(b) * per_slot + rem) * N;
+    const float* yi = p.y_im + (size_t(b) * per_slot + rem) * N;
+    for (int u = 0; u < p.U; ++u) {
+        const int k = __ldg(p.nn_prb + size_t(u) * per_slot + rem);
+        const size_t h0 = ((size_t(b) * p.n_pilots + k) * p.U + u) * N;
+        const size_t h1 = ((size_t(b) * p.n_pilots + (k ^ 1)) * p.U + u) * N;   // FOCC partner (:1620-1629)
+        const float2 pe = *reinterpret_cast<const float2*>(p.pos_enc + (size_t(u) * per_slot + rem) * 2);
+        __align__(16) __half row[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) row[c] = __float2half(0.f);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+            if (a < N) {
+                row[a] = __float2half(__ldg(yr + a) * g);
+                row[N + a] = __float2half(__ldg(yi + a) * g);
+                row[2 * N + 2 + a] = __float2half(0.5f * (__ldg(p.h_re + h0 + a) + __ldg(p.h_re + h1 + a)) * g);
+                row[3 * N + 2 + a] = __float2half(0.5f * (__ldg(p.h_im + h0 + a) + __ldg(p.h_im + h1 + a)) * g);
+            }
+        row[2 * N] = __float2half(pe.x);
+        row[2 * N + 1] = __float2half(pe.y);
+        const size_t prow = (size_t(bl) * p.U + u) * per_slot + rem;
+        uint4* dst = reinterpret_cast<uint4*>(p.z0 + prow * 32);
+        const uint4* srcv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = srcv[c];
+    }
+}
+
+// =============================================================================================
 // 3. separable-conv layer: depthwise 3x3 (CUDA cores, HFMA2) -> swizzled A operand in smem ->
 //    pointwise GEMM on tcgen05 (fp32 accumulators in TMEM) -> bias / ReLU / residual epilogue
 //    (Keras SeparableConv2D of StateInit utils/neural_rx.py:61-132 and UpdateState :210-270)
@@ -607,6 +684,7 @@ struct ReadoutParams {
     float* llr;                  // [Bp][U][n_data*out_bits] or null
     float* llr_grid;             // [Bp][U][F][T][out_bits]  or null
     float* h_ref;                // [Bp][U][F][T][2N]        or null
+    float* llr_aerial;           // [Bp][out_bits][U][F][T] = -LLR (NeuralReceiverONNX, :1809-1810) or null
     int F, U, N2, out_bits, n_data;
     int rows_per_bu, tiles_per_bu, num_tiles, default_head;
 };
@@ -729,6 +807,13 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
                         for (int j = 0; j < 16; ++j)
                             if (j < p.out_bits) o[j] = v[j];
                     }
+                }
+                if (p.llr_aerial) {
+                    const int bb = bu / p.U, uu = bu - bb * p.U;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < p.out_bits)
+                            p.llr_aerial[((size_t(bb) * p.out_bits + j) * p.U + uu) * p.rows_per_bu + prow] = -v[j];
                 }
                 if (p.h_ref) {
                     float* o = p.h_ref + grow * p.N2;

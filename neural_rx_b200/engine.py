@@ -23,7 +23,7 @@ NRX_MAX_DMRS = 4
 #: every symbol declared in include/nrx_b200.h
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
-    "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_launches_per_forward",
+    "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
 
@@ -85,6 +85,9 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                 ctypes.c_void_p, ctypes.c_size_t]
     lib.nrx_forward_host.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p, i32p, i32p,
                                      ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p]
+    lib.nrx_set_aerial_dmrs.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int32, i32p, ctypes.c_int32]
+    lib.nrx_forward_aerial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, f32p, f32p, f32p, f32p, f32p,
+                                       f32p, f32p, ctypes.c_void_p, ctypes.c_size_t]
     lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
@@ -275,6 +278,52 @@ class NrxEngine:
         res["_keepalive"] = (y, active_tx, io_t, head_t)
         del per
         return res
+
+    # ---- Aerial / TensorRT-shaped call (NeuralReceiverONNX.forward, utils/neural_rx.py:1773-1812) ----
+    def set_aerial_dmrs(self, dmrs_ofdm_pos, dmrs_subcarrier_pos) -> None:
+        op = np.ascontiguousarray(dmrs_ofdm_pos, dtype=np.int32)
+        sp = np.ascontiguousarray(dmrs_subcarrier_pos, dtype=np.int32)
+        U = self.grid.num_tx
+        if op.ndim != 2 or sp.ndim != 2 or op.shape[0] != U or sp.shape[0] != U:
+            raise ValueError(f"dmrs_ofdm_pos / dmrs_subcarrier_pos must be [{U}, n]")
+        self._check(self._lib.nrx_set_aerial_dmrs(self._h, op.ctypes.data, op.shape[1], sp.ctypes.data, sp.shape[1]))
+        self._aerial_key = (op.tobytes(), sp.tobytes())
+        self._aerial_pilots = op.shape[1] * (self.grid.num_subcarriers // 12) * sp.shape[1]
+
+    def forward_aerial(self, rx_slot_real, rx_slot_imag, h_hat_real, h_hat_imag, active_dmrs_ports,
+                       dmrs_ofdm_pos, dmrs_subcarrier_pos, stream=None):
+        """float32 CUDA tensors rx_slot_* [B,F,T,N_rx], h_hat_* [B,n_pilots,U,N_rx],
+        active_dmrs_ports [B,U]; integer host arrays dmrs_ofdm_pos [U,n_sym], dmrs_subcarrier_pos
+        [U,n_sc].  Returns (llr [B,bits,U,F,T] = -LLR, h_hat [B,U,F,T,2N_rx]) CUDA tensors."""
+        import torch
+
+        op = np.ascontiguousarray(np.asarray(dmrs_ofdm_pos), dtype=np.int32)
+        sp = np.ascontiguousarray(np.asarray(dmrs_subcarrier_pos), dtype=np.int32)
+        if getattr(self, "_aerial_key", None) != (op.tobytes(), sp.tobytes()):
+            self.set_aerial_dmrs(op, sp)
+        g, N = self.grid, self.cfg.num_rx_antennas
+        B, U, F, T = int(rx_slot_real.shape[0]), g.num_tx, g.num_subcarriers, g.num_ofdm_symbols
+        ts = [rx_slot_real, rx_slot_imag, h_hat_real, h_hat_imag, active_dmrs_ports]
+        shapes = [(B, F, T, N), (B, F, T, N), (B, self._aerial_pilots, U, N), (B, self._aerial_pilots, U, N), (B, U)]
+        for i, (t, sh) in enumerate(zip(ts, shapes)):
+            if tuple(t.shape) != sh:
+                raise ValueError(f"input {i} must have shape {sh}, got {tuple(t.shape)}")
+            if not t.is_cuda or t.device.index != self.device:
+                raise ValueError("inputs must live on the engine's CUDA device")
+            ts[i] = t.to(dtype=torch.float32).contiguous()
+        dev = ts[0].device
+        bits = self.cfg.readout_bits[0]
+        llr = torch.empty((B, bits, U, F, T), dtype=torch.float32, device=dev)
+        h = torch.empty((B, U, F, T, 2 * N), dtype=torch.float32, device=dev)
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        self._check(self._lib.nrx_forward_aerial(self._h, ctypes.c_void_p(st), B, ts[0].data_ptr(), ts[1].data_ptr(),
+                                                 ts[2].data_ptr(), ts[3].data_ptr(), ts[4].data_ptr(), llr.data_ptr(),
+                                                 h.data_ptr(), self._ws.data_ptr(), self._ws.numel()))
+        self._aerial_keepalive = ts
+        return llr, h
 
     # ---- host call (NumPy arrays, H2D + D2H inside) --------------------------------------------
     def forward_host(self, y: np.ndarray, active_tx: np.ndarray, io_index=None, head_index=None,

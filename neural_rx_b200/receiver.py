@@ -129,6 +129,62 @@ class NeuralPUSCHReceiver:
     forward = __call__
 
 
+class NeuralReceiverONNX:
+    """Aerial / TensorRT-shaped wrapper — ``NeuralReceiverONNX`` of ``utils/neural_rx.py:1716-1812``
+    (the model ``scripts/export_onnx.py`` exports; binding names ``:153-160``).
+
+    ``forward([rx_slot_real, rx_slot_imag, h_hat_real, h_hat_imag, active_dmrs_ports,
+    dmrs_ofdm_pos, dmrs_subcarrier_pos])`` -> ``(llr [B,bits,U,F,T], h_hat [B,U,F,T,2N_rx])`` with
+    the Aerial LLR sign (minus the Sionna convention, ``:1809-1810``).  Inputs are NumPy arrays
+    (copied to the device and back) or torch CUDA tensors (outputs stay on the device).  Built
+    from the receiver configuration instead of the reference's positional layer-size arguments;
+    single-MCS configurations only, as in the reference (``:1796``)."""
+
+    def __init__(self, sys_parameters: Union[NrxConfig, str], weights: Optional[NrxWeights] = None,
+                 n_size_bwp: Optional[int] = None, device: int = 0):
+        cfg = get_config(sys_parameters) if isinstance(sys_parameters, str) else sys_parameters
+        cfg.validate()
+        if cfg.num_mcss_supported != 1:
+            raise NotImplementedError("NeuralReceiverONNX has no support for mixed MCS")
+        self._sys_parameters = cfg
+        self._grid = build_grid(cfg, n_size_bwp=n_size_bwp)
+        self._weights = random_weights(cfg) if weights is None else weights
+        self._engine = NrxEngine(cfg, self._weights, self._grid, device)
+        self._num_it = cfg.num_nrx_iter_eval
+        self._engine.num_it = self._num_it
+
+    @property
+    def engine(self) -> NrxEngine:
+        return self._engine
+
+    @property
+    def num_it(self) -> int:
+        return self._num_it
+
+    @num_it.setter
+    def num_it(self, val: int) -> None:
+        assert 1 <= val <= self._sys_parameters.num_nrx_iter, "Invalid number of iterations"   # :1766-1771
+        self._num_it = int(val)
+        self._engine.num_it = self._num_it
+
+    def forward(self, inputs):
+        import torch
+
+        y_re, y_im, h_re, h_im, port_mask, ofdm_pos, sc_pos = inputs
+        on_host = isinstance(y_re, np.ndarray)
+        dev = torch.device("cuda", self._engine.device)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev) if on_host else a
+        to_np = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+        llr, h = self._engine.forward_aerial(t(y_re), t(y_im), t(h_re), t(h_im), t(port_mask), to_np(ofdm_pos),
+                                             to_np(sc_pos))
+        if on_host:
+            torch.cuda.synchronize(dev)
+            return llr.cpu().numpy(), h.cpu().numpy()
+        return llr, h
+
+    __call__ = forward
+
+
 def load_weights(receiver: NeuralPUSCHReceiver, model_path: str) -> None:
     """``utils.load_weights(model, path)``: unpickle the Keras weight list and set it."""
     receiver.set_weights(_load_weight_file(receiver._sys_parameters, model_path))

@@ -154,3 +154,29 @@ def uncoded_ber(llr: np.ndarray, bits: np.ndarray, active_tx: np.ndarray, num_bi
     err = (hard != bits[..., :n]).astype(np.float64)
     w = np.broadcast_to(active_tx[..., None], err.shape)
     return float((err * w).sum() / max(w.sum(), 1.0))
+
+
+def aerial_inputs(sb, grid):
+    """Re-shape a synthetic slot batch into the seven inputs of the Aerial / TensorRT-shaped
+    receiver (what ``utils/onnx_utils.py:376-409`` does with the Sionna tensors): rx_slot
+    [B,F,T,N_rx] real / imag, raw LS estimates ``y_p / p`` at every user's non-zero pilots
+    [B,n_pilots,U,N_rx] (DMRS-symbol major, zero pilots dropped), the active-port mask and the DMRS
+    symbol / in-PRB subcarrier positions."""
+    y = np.transpose(sb.y[:, 0], (0, 3, 2, 1))                                # [B,F,T,N]
+    U, F = grid.num_tx, grid.num_subcarriers
+    ofdm_pos = np.tile(np.asarray(grid.dmrs_symbols, np.int32), (U, 1))
+    hs, sc_pos = [], []
+    for u in range(U):
+        h_sym = []
+        nz0 = None
+        for j, l in enumerate(grid.dmrs_symbols):
+            p = grid.pilots[u, j * F:(j + 1) * F]
+            nz = np.flatnonzero(np.abs(p) > 0)
+            nz0 = nz if nz0 is None else nz0
+            h_sym.append(sb.y[:, 0, :, l, :][:, :, nz] / p[nz])               # [B,N,n_nz]
+        hs.append(np.concatenate(h_sym, axis=-1))                             # [B,N,n_pilots]
+        sc_pos.append(nz0[nz0 < 12])
+    h = np.transpose(np.stack(hs, axis=1), (0, 3, 1, 2))                      # [B,n_pilots,U,N]
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return [f32(y.real), f32(y.imag), f32(h.real), f32(h.imag), f32(sb.active_tx), ofdm_pos,
+            np.asarray(sc_pos, np.int32)]

@@ -375,3 +375,79 @@ def receiver_forward(net, arch: OracleArch, y, pilots, pilot_mask, active_tx,
     llr_grid = [l.float().numpy() for l in llrs]
     return dict(llr=demap_llrs(llr_grid[mcs_arr_eval[0]], pilot_mask), llr_grid=llr_grid,
                 h_hat_refined=h_ref.float().numpy(), h_hat=h_hat)
+
+
+# --------------------------------------------------------------------------------------------
+# Aerial / TensorRT-shaped entry point (NRPreprocessing + NeuralReceiverONNX,
+# utils/neural_rx.py:1614-1812; binding names scripts/export_onnx.py:153-160)
+# --------------------------------------------------------------------------------------------
+def aerial_nn_indices(dmrs_ofdm_pos: np.ndarray, dmrs_subcarrier_pos: np.ndarray, T: int):
+    """``NRPreprocessing._calculate_nn_indices`` (utils/neural_rx.py:1631-1670) on the 12 x T
+    template of one PRB.  Pilot candidates are enumerated subcarrier-major / symbol-minor (the
+    ``meshgrid(dmrs_subcarrier_pos, dmrs_ofdm_pos)`` order, :1643-1644); the nearest one in
+    Manhattan distance wins, ties -> first.  Returns (k_idx, j_idx) [U, 12, T]: index of the
+    chosen pilot subcarrier (within the PRB's list) and of its DMRS symbol; and the positional
+    encoding [U, 12, T, 2] = (time, freq) distance to the nearest pilot per axis, each centred
+    and divided by (population std + 1e-8) over the template (:1654-1660; the fork's torch
+    ``.std()`` is the unbiased estimator, the TF original used ``reduce_std`` — SURVEY.md App. B)."""
+    U, n_sc = dmrs_subcarrier_pos.shape
+    n_sym = dmrs_ofdm_pos.shape[1]
+    k_idx = np.zeros((U, 12, T), np.int32)
+    j_idx = np.zeros((U, 12, T), np.int32)
+    pe = np.zeros((U, 12, T, 2), np.float64)
+    for u in range(U):
+        sc_p = np.repeat(dmrs_subcarrier_pos[u], n_sym)              # subcarrier-major candidate list
+        t_p = np.tile(dmrs_ofdm_pos[u], n_sc)
+        for sc in range(12):
+            for t in range(T):
+                d_sc, d_t = np.abs(sc - sc_p), np.abs(t - t_p)
+                i = int(np.argmin(d_sc + d_t))
+                k_idx[u, sc, t], j_idx[u, sc, t] = i // n_sym, i % n_sym
+                pe[u, sc, t] = (d_t.min(), d_sc.min())
+        for c in range(2):
+            x = pe[u, ..., c]
+            pe[u, ..., c] = (x - x.mean()) / (x.std() + 1e-8)
+    return k_idx, j_idx, pe.astype(np.float32)
+
+
+def aerial_preprocess(h_hat_p: np.ndarray, dmrs_ofdm_pos: np.ndarray, dmrs_subcarrier_pos: np.ndarray, T: int):
+    """``NRPreprocessing.forward`` (utils/neural_rx.py:1700-1713).
+
+    h_hat_p [B, n_pilots, U, 2*N_rx] (re | im): LS estimates at the non-zero pilots of every user,
+    DMRS-symbol-major, subcarrier ascending (how utils/onnx_utils.py:384-397 builds the input).
+      1. FOCC removal: adjacent pilot pairs are replaced by their mean (:1620-1629)
+      2. per-PRB nearest-neighbour interpolation (:1672-1698)
+    -> h_hat [B, U, F, T, 2*N_rx], pe [U, F, T, 2]."""
+    B, n_p, U, C = h_hat_p.shape
+    n_sym, n_sc = dmrs_ofdm_pos.shape[1], dmrs_subcarrier_pos.shape[1]
+    n_prb = n_p // (n_sym * n_sc)
+    Fs = 12 * n_prb
+    h = h_hat_p.reshape(B, n_p // 2, 2, U, C)
+    h = np.repeat(h.sum(axis=2, keepdims=True) / 2.0, 2, axis=2).reshape(B, n_sym, n_prb, n_sc, U, C)
+    k_idx, j_idx, pe12 = aerial_nn_indices(dmrs_ofdm_pos, dmrs_subcarrier_pos, T)
+    out = np.zeros((B, U, Fs, T, C), np.float32)
+    for u in range(U):
+        for sc in range(12):
+            for t in range(T):
+                out[:, u, sc::12, t, :] = h[:, j_idx[u, sc, t], :, k_idx[u, sc, t], u, :]
+    return out, np.tile(pe12, (1, n_prb, 1, 1))
+
+
+def aerial_forward(net, arch: OracleArch, rx_real, rx_imag, h_real, h_imag, active_ports,
+                   dmrs_ofdm_pos, dmrs_subcarrier_pos, num_it=None, dtype=torch.float32,
+                   emu: Emulation = EXACT):
+    """``NeuralReceiverONNX.forward`` (utils/neural_rx.py:1773-1812): rx_slot_* [B,F,T,N_rx],
+    h_hat_* [B,n_pilots,U,N_rx], active_dmrs_ports [B,U] -> llr [B,bits,U,F,T] (= -LLR of the
+    Sionna-shaped call, :1809-1810) and h_hat [B,U,F,T,2*N_rx]."""
+    y = np.concatenate([rx_real, rx_imag], axis=-1).astype(np.float32)       # :1787
+    h_p = np.concatenate([h_real, h_imag], axis=-1).astype(np.float32)
+    T = y.shape[2]
+    h_hat, pe = aerial_preprocess(h_p, np.asarray(dmrs_ofdm_pos), np.asarray(dmrs_subcarrier_pos), T)
+    B, U = h_hat.shape[:2]
+    mask = np.ones((B, U, 1), np.float32)                                     # :1796 (single MCS)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
+    with torch.no_grad():
+        llrs, h_ref = cgnn_forward(net, arch, t(y), t(pe), t(h_hat), t(active_ports), t(mask),
+                                   num_it=num_it, emu=emu)
+    llr = llrs[0].float().numpy()                                             # [B,U,F,T,bits]
+    return dict(llr=-np.transpose(llr, (0, 4, 1, 2, 3)), h_hat=h_ref.float().numpy(), h_hat_ls=h_hat, pe=pe)

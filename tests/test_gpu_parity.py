@@ -115,6 +115,35 @@ def test_fused_equals_layerwise(label, n_prb, batch):
         assert rel_l2(outs[2]["llr"], ref["llr"]) <= TOL_EXACT
 
 
+@pytest.mark.parametrize("num_tx,ports,active", [(1, [[0]], [[1]]), (3, [[0], [2], [1]], [[1, 1, 1], [1, 0, 1]]),
+                                                  (4, [[0], [2], [1], [3]], [[1, 1, 1, 1], [0, 1, 1, 0]])])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_other_user_counts(num_tx, ports, active, fused):
+    """1, 3 and 4 users (AggregateUserStates general form: masked sum over the other users and the
+    1 / max(n_active - 1, 1) scaling, utils/neural_rx.py:192-204; single-UE shapes).
+    The reference ships weights for 2-UE training only; the layer shapes do not depend on the
+    user count, so seeded random weights of the nrx_rt architecture are used."""
+    import dataclasses
+    cfg = dataclasses.replace(get_config("nrx_rt"), max_num_tx=num_tx, dmrs_port_sets=ports)
+    cfg.validate()
+    weights, _ = get_weights(cfg, prefer_real=False, seed=11)
+    grid = build_grid(cfg, n_size_bwp=5)
+    act = np.asarray(active, np.float32)
+    act = np.broadcast_to(act.reshape(-1, num_tx), (2, num_tx)).copy()
+    sb = make_slots(cfg, grid, batch=2, ebno_db=9.0, seed=300 + num_tx, active=act)
+    eng = _engine(cfg, weights, grid, fused=fused)
+    got = _run(eng, sb)
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx)
+    emu = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx, emu=ENGINE_EMU)
+    assert got["llr"].shape == ref["llr"].shape
+    assert rel_l2(got["h_hat"], ref["h_hat"]) <= 1e-5
+    assert rel_l2(got["llr"], ref["llr"]) <= TOL_EXACT
+    assert rel_l2(got["llr"], emu["llr"]) <= TOL_EMUL
+    assert rel_l2(got["h_hat_refined"], ref["h_hat_refined"]) <= TOL_EXACT
+    eng.close()
+
+
 def test_random_weights_parity():
     """Seeded random-init weights (always available, unlike the staged weight files)."""
     cfg = get_config("nrx_rt")
@@ -329,3 +358,40 @@ def test_golden_fixture(name, label):
     assert rel_l2(got["h_hat"], g["h_hat"]) <= 1e-5
     assert rel_l2(got["h_hat_refined"], g["h_hat_refined"]) <= TOL_EXACT
     eng.close()
+
+
+@pytest.mark.parametrize("label,n_prb,batch", [("nrx_rt", 4, 2), ("nrx_large_64qam", 6, 1), ("nrx_rt", 132, 1)])
+def test_aerial_shaped_entry(label, n_prb, batch):
+    """NeuralReceiverONNX.forward (utils/neural_rx.py:1773-1812): TRT-binding-shaped inputs, FOCC
+    removal and per-PRB nearest-pilot interpolation of NRPreprocessing (:1614-1713), LLRs in the
+    Aerial layout [B,bits,U,F,T] with the Aerial sign."""
+    from neural_rx_b200.receiver import NeuralReceiverONNX
+    from neural_rx_b200.synth import aerial_inputs
+    cfg = get_config(label)
+    weights, _ = get_weights(cfg)
+    rx = NeuralReceiverONNX(cfg, weights=weights, n_size_bwp=n_prb)
+    grid = build_grid(cfg, n_size_bwp=n_prb)
+    sb = make_slots(cfg, grid, batch=batch, ebno_db=9.0, seed=400 + n_prb)
+    ins = aerial_inputs(sb, grid)
+    llr, h = rx(ins)
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    ref = O.aerial_forward(net, arch, *ins)
+    emu = O.aerial_forward(net, arch, *ins, emu=ENGINE_EMU)
+    assert llr.shape == ref["llr"].shape == (batch, cfg.num_bits_per_symbol[0], 2, grid.num_subcarriers, 14)
+    assert rel_l2(llr, ref["llr"]) <= TOL_EXACT
+    assert sign_agreement(llr, ref["llr"]) >= TOL_AGREE
+    assert rel_l2(h, ref["h_hat"]) <= TOL_EXACT
+    assert rel_l2(llr, emu["llr"]) <= TOL_EMUL
+    # same receiver through the Sionna-shaped call: LLRs of UE 0 agree up to the sign / layout
+    # (its interpolation is identical); the sign convention is flipped (:1809-1810)
+    import torch
+    out = rx.engine.forward(torch.as_tensor(sb.y).cuda(), torch.as_tensor(sb.active_tx).cuda(), want=("llr_grid",))
+    g0 = out["llr_grid"].cpu().numpy()                                    # [B,U,F,T,bits]
+    assert sign_agreement(-np.transpose(llr, (0, 2, 3, 4, 1))[:, 0], g0[:, 0]) >= 0.98
+    # torch tensors in -> torch tensors out, same numbers
+    tin = [torch.as_tensor(a).cuda() for a in ins[:5]] + ins[5:]
+    llr_t, h_t = rx(tin)
+    assert np.array_equal(llr_t.cpu().numpy(), llr) and np.array_equal(h_t.cpu().numpy(), h)
+    rx.num_it = 1
+    with pytest.raises(AssertionError, match="Invalid number of iterations"):
+        rx.num_it = cfg.num_nrx_iter + 1

@@ -191,3 +191,24 @@ def test_oracle_invariances():
     sp = s.reshape(1, 2, 4, 14, 56) * act[:, :, None, None, None]
     a = sp.sum(1, keepdim=True) - sp
     assert torch.all(a[0, 0] == 0) and torch.equal(a[0, 1], sp[0, 0])
+
+
+def test_aerial_preprocessing_matches_documented_semantics():
+    """NRPreprocessing (utils/neural_rx.py:1614-1713) vs the Sionna-shaped estimator: identical for
+    the even-comb user; for the odd-comb user only the first subcarrier of every PRB but the first
+    differs (per-PRB template takes f+1 where the global rule takes f-1); the positional encoding
+    of the tiled 12 x T template equals the global one."""
+    from neural_rx_b200.config import get_config
+    from neural_rx_b200.pusch import build_grid
+    from neural_rx_b200.synth import aerial_inputs, make_slots
+    cfg = get_config("nrx_rt")
+    grid = build_grid(cfg, n_size_bwp=3)
+    sb = make_slots(cfg, grid, batch=2, ebno_db=8.0, seed=4)
+    ins = aerial_inputs(sb, grid)
+    assert ins[2].shape == (2, grid.num_subcarriers, 2, 4)                # TRT binding h_hat: [B, n_pilots = F, U, N_rx]
+    h, pe = O.aerial_preprocess(np.concatenate([ins[2], ins[3]], -1), ins[5], ins[6], 14)
+    r = O.ls_channel_estimate(sb.y, grid.pilots, grid.pilot_mask)
+    assert np.array_equal(h[:, 0], r[:, 0])
+    d = np.abs(h[:, 1] - r[:, 1]).max(axis=(0, 2, 3))
+    assert list(np.flatnonzero(d > 0)) == [12, 24]
+    assert np.abs(pe - grid.pos_enc).max() < 1e-6
