@@ -561,18 +561,36 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(Agg
     const int q = warp & 3, hcol = warp >> 2;
     const int r = q * 32 + lane;
 
+    // The state rows of the NEXT tile are fetched into registers while the current tile is processed
+    // (software pipelining: the global-load latency used to be exposed in front of every tile).
+    constexpr int NV = U * 128 * 8 / kThreads;        // 16-byte vectors per thread per tile
+    uint4 pre[NV];
+    auto fetch = [&](int tile) {
+        const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
+        const int r0 = rt * 128, valid_rows = min(128, p.rows_per_bu - r0);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int i = tid + v * kThreads;
+            const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
+            pre[v] = make_uint4(0, 0, 0, 0);
+            if (rr < valid_rows)
+                pre[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
+        }
+    };
+    if (int(blockIdx.x) < p.num_tiles) fetch(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
-        // ---- stage the state rows of all users into swizzled A tiles ------------------------
-        for (int i = tid; i < U * 128 * 8; i += kThreads) {
+        // ---- stage the (prefetched) state rows of all users into swizzled A tiles -----------
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int i = tid + v * kThreads;
             const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (rr < valid_rows)
-                val = *reinterpret_cast<const uint4*>(p.sbuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8);
-            st_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4), val);
+            st_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
         }
+        if (tile + int(gridDim.x) < p.num_tiles) fetch(tile + gridDim.x);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -720,6 +738,23 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
     const int q = warp & 3, hcol = warp >> 2;
     const int r = q * 32 + lane;
 
+    // next tile's state rows prefetched into registers while the current tile is processed
+    constexpr int NV = 128 * 8 / kThreads;
+    uint4 pre[NV];
+    auto fetch = [&](int tile) {
+        const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
+        const int r0 = rt * 128, valid_rows = min(128, p.rows_per_bu - r0);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int i = tid + v * kThreads;
+            const int rr = i >> 3, cc = i & 7;
+            pre[v] = make_uint4(0, 0, 0, 0);
+            if (rr < valid_rows)
+                pre[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
+        }
+    };
+    if (int(blockIdx.x) < p.num_tiles) fetch(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
         const int r0 = rt * 128;
@@ -735,13 +770,13 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
             ph_w ^= 1;
             loaded_head = head;
         }
-        for (int i = tid; i < 128 * 8; i += kThreads) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int i = tid + v * kThreads;
             const int rr = i >> 3, cc = i & 7;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (rr < valid_rows)
-                val = *reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8);
-            st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), val);
+            st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
         }
+        if (tile + int(gridDim.x) < p.num_tiles) fetch(tile + gridDim.x);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
