@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots-per-pass", type=int, default=int(os.environ.get("NRX_SLOTS_PER_PASS", "0")))
+    ap.add_argument("--fused", type=int, default=int(os.environ.get("NRX_FUSED", "1")),
+                    help="execution plan of the sep-conv stacks (nrx_set_fused)")
     ap.add_argument("--host-chunk", type=int, default=int(os.environ.get("NRX_HOST_CHUNK", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -204,6 +206,7 @@ def main():
     eng = NrxEngine(cfg, weights, grid, device=local_rank)
     if args.slots_per_pass:
         eng.set_slots_per_pass(args.slots_per_pass)
+    eng.set_fused(args.fused)
 
     # distinct synthetic batches per rank; rotating over NBUF x 21 MB of inputs (> 126 MB L2)
     NBUF = 8

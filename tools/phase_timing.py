@@ -33,6 +33,7 @@ sb = make_slots(cfg, grid, batch=1, ebno_db=4.0, seed=1)
 y = torch.as_tensor(np.repeat(sb.y, batch, axis=0)).cuda()
 act = torch.ones((batch, 2), device="cuda")
 eng = E.NrxEngine(cfg, w, grid)
+eng.set_fused(int(os.environ.get("NRX_FUSED", "1")))
 lib = E.load_library()
 buf = (ctypes.c_ulonglong * 32)()
 for _ in range(2):
@@ -47,8 +48,8 @@ lib.nrx_debug_phase_cycles(buf)
 names = ["z wait+sync", "L1 dw", "L1 sync", "L1 issue+prefetch", "L1 mma wait", "L1 epilogue", "L1 sync",
          "L2 dw", "L2 sync", "L2 issue+carry", "L2 mma wait", "L2 epilogue", "L2 sync",
          "L3 dw", "L3 sync", "L3 issue+carry+prefetch", "L3 mma wait", "L3 epilogue(stage)", "L3 sync",
-         "copy-out", "copy-out sync", "item/loop overhead"]
-tot = sum(buf[i] for i in range(22))
+         "copy-out", "copy-out sync", "item/loop overhead", "wait for helper warps (ws kernel)"]
+tot = sum(buf[i] for i in range(23))
 print(f"{label} batch {batch}: total cycles CTA0 over {n_fwd} forwards = {tot}")
 for i, n in enumerate(names):
     print(f"  {n:26s} {buf[i]:12d}  {100.0 * buf[i] / max(tot, 1):5.1f}%")
