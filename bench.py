@@ -274,8 +274,18 @@ def main():
         flops_per_launch = 2.0 * mac_layer[dom] * pixels_per_launch
         dur_s = prof[dom]["ms"] * 1e-3 / n_l
         achieved = flops_per_launch / dur_s / 1e12
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same workload)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        ncu_name = {"stack_update": "nrx_stack_kernel<1, 0>", "stack_init": "nrx_stack_kernel<0, 0>",
+                    "agg": "nrx_agg_kernel<2>", "readout": "nrx_readout_kernel"}.get(dom)
+        if os.path.exists(tpath) and ncu_name and passes == 1 and args.fused == 1:
+            with open(tpath) as f:
+                traffic = json.load(f).get(ncu_name, {}).get("dram_bytes_per_launch")
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "algorithmic_bytes_per_launch": 512.0 * pixels_per_launch if dom == "stack_update" else None,
+                "peak_source": peak_src,
                 "launch_us": dur_s * 1e6, "launches_per_step": launches_per_step,
                 "share_of_kernel_time": prof[dom]["ms"] / max(total_kernel_ms, 1e-9)}
     whole = {"achieved_tflops": eng.flops_per_slot() * value / world / 1e12,
