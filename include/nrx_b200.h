@@ -95,10 +95,6 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  *                         (:184-188) runs in the tail of the preceding stack, each user reads the
  *                         other user's message tensor directly and no aggregation kernel is
  *                         launched (measured on B200: same speed as plan 1);
- *   fused == 3:           as 1 with the warp-specialised stack kernel: four helper warps take
- *                         the layer-3 epilogue, residual and store off the main warps' chain
- *                         (measured on B200: 3 % slower than plan 1 — the helpers' shared-memory
- *                         traffic slows the concurrent depthwise pass by what they save);
  *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
  * All plans compute the same function; the others are kept as cross-checks. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);

@@ -16,7 +16,6 @@
 #include "../../include/nrx_b200.h"
 #include "nrx_kernels.cuh"
 #include "nrx_stack.cuh"
-#include "nrx_stack_ws.cuh"
 
 using namespace nrx;
 
@@ -73,8 +72,7 @@ struct nrx_engine {
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
     int fused = 1;                                  // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
-                                                    // MLP in their tail (two users only), 3: as 1 with the warp-specialised
-                                                    // stack kernel (helper warps), 0: layer-per-kernel
+                                                    // MLP in their tail (two users only), 0: layer-per-kernel
     int32_t* nn_index = nullptr;
     FoccEntry* focc = nullptr;
     float* pos_enc = nullptr;
@@ -512,8 +510,6 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_readout_kernel, kRoSmem));
     acc(set_smem(nrx_stack_kernel<kStackInit, false>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, false>, StackSmem<kStackUpdate>::kTotal));
-    acc(set_smem(nrx_stack_ws_kernel<kStackInit>, StackSmem<kStackInit>::kTotal));
-    acc(set_smem(nrx_stack_ws_kernel<kStackUpdate>, StackSmem<kStackUpdate>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
@@ -559,7 +555,7 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    if (fused < 0 || fused > 3) return fail(NRX_ERR_INVALID, "fused must be 0, 1, 2 or 3");
+    if (fused < 0 || fused > 2) return fail(NRX_ERR_INVALID, "fused must be 0, 1 or 2");
     e->fused = fused;
     return NRX_OK;
 }
@@ -669,7 +665,6 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
             // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
             const bool pair = U == 2 && e->fused == 2;
-            const bool helpers = e->fused == 3;          // warp-specialised stack kernel (helper warps own the output side)
             __half* sp_cur = abuf;
             __half* sp_alt = reinterpret_cast<__half*>(ws + w.abuf2);
             kp.z0 = z0; kp.s_out = s_cur;
@@ -682,7 +677,6 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             {
                 Timed t(e, st, NRX_K_STACK_INIT);
                 if (pair) nrx_stack_kernel<kStackInit, true><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
-                else if (helpers) nrx_stack_ws_kernel<kStackInit><<<sgrid, kWsThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
                 else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
             kp.stack_index = nullptr;
@@ -697,7 +691,6 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
                 {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
-                    else if (helpers) nrx_stack_ws_kernel<kStackUpdate><<<sgrid, kWsThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                     else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                 }
                 __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
