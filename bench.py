@@ -42,10 +42,9 @@ UNIT = "slots/s"
 
 
 def _weights(cfg):
-    for d in (os.path.join(ROOT, "weights"), "/root/reference/weights"):
-        p = os.path.join(d, f"{cfg.label}_weights")
-        if os.path.exists(p):
-            return load_weights(cfg, p), "shipped weight file"
+    p = os.path.join(ROOT, "weights", f"{cfg.label}_weights")      # staged copy of the reference's weight file
+    if os.path.exists(p):
+        return load_weights(cfg, p), "shipped weight file"
     return random_weights(cfg, seed=0), "random-init weights"
 
 

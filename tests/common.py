@@ -12,7 +12,7 @@ from neural_rx_b200.weights import NrxWeights, load_weights, random_weights
 from oracle import nrx_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WEIGHT_DIRS = [os.path.join(ROOT, "weights"), "/root/reference/weights"]
+WEIGHT_DIRS = [os.path.join(ROOT, "weights")]      # staged (git-ignored) copies of the reference's weight files
 
 #: emulation of where the CUDA engine rounds (fp16 operands everywhere, fp32 accumulate in GEMMs)
 ENGINE_EMU = O.Emulation(act_fp16=True, weight_fp16=True, dw_weight_fp16=True, dw_acc_fp16=True, state_fp16=True)
