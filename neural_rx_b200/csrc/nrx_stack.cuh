@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
     };
 
     bool z_prefetched = false;                          // the next item's first window is already in flight
+    bool w_pending = false;                             // a weight blob load has been issued and not yet waited for
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
@@ -303,8 +304,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
                 mbar_arrive_expect_tx(&bar_w, L::kBlob);
                 bulk_g2s(sW, p.wblob + size_t(stack) * L::kBlob, L::kBlob, &bar_w);
             }
-            mbar_wait(&bar_w, ph_w);
-            ph_w ^= 1;
+            w_pending = true;                          // waited for after the first input window has been requested
             loaded_stack = stack;
         }
         // message source plane: the aggregated tensor of this user, or (two-user fast path) the
@@ -454,6 +454,11 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 
         if (!z_prefetched) stage_z(c0 - kRunIn + 1);
         z_prefetched = false;
+        if (w_pending) {                               // weights land while the window is in flight
+            mbar_wait(&bar_w, ph_w);
+            ph_w ^= 1;
+            w_pending = false;
+        }
         for (int k = 0; k < nsteps; ++k) {
             const int b = c0 - kRunIn + kStepF * k;
             NRX_TICK(21);                               // item set-up / loop overhead
