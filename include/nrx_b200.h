@@ -95,6 +95,12 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  *                         (:184-188) runs in the tail of the preceding stack, each user reads the
  *                         other user's message tensor directly and no aggregation kernel is
  *                         launched (measured on B200: same speed as plan 1);
+ *   fused == 3:           as 1, but (two users) the two users of a slot run in the two CTAs of a
+ *                         cluster and the pointwise GEMMs are issued for the pair with
+ *                         tcgen05.mma.cta_group::2 — each CTA holds half of every weight matrix.
+ *                         Bit-identical; measured 31 % slower than plan 1 because the two
+ *                         cluster-scope hand-shakes per GEMM sit on the serial chain.  Kept as the
+ *                         base of the next kernel generation (ROADMAP.md);
  *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
  * All plans compute the same function; the others are kept as cross-checks. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);

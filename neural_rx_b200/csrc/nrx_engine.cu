@@ -17,6 +17,7 @@
 #include "../../include/nrx_b200.h"
 #include "nrx_kernels.cuh"
 #include "nrx_stack.cuh"
+#include "nrx_stack_pair.cuh"
 
 using namespace nrx;
 
@@ -91,8 +92,11 @@ struct nrx_engine {
     uint8_t* readout_blob = nullptr;                // [n_io] heads
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
+    uint8_t* pair_init_blob = nullptr;              // CTA-pair kernels: [n_io][2 ranks] half-weight images
+    std::vector<uint8_t*> pair_upd_blobs;           // [it] -> [2 ranks]
     int fused = 1;                                  // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
-                                                    // MLP in their tail (two users only), 0: layer-per-kernel
+                                                    // MLP in their tail (two users only), 3: CTA-pair stack kernels
+                                                    // (experimental), 0: layer-per-kernel
     int32_t* nn_index = nullptr;
     FoccEntry* focc = nullptr;
     float* pos_enc = nullptr;
@@ -202,6 +206,31 @@ void pack_stack_agg(uint8_t* b, const float* const* arrays, int first, int d_s, 
     for (int n = 0; n < d_s; ++n) bias[64 + n] = arrays[first + 3][n];
 }
 
+// Per-rank weight image of the CTA-pair stack kernel (StackPairSmem<MODE>): rank r holds output channels
+// [r*N/2, (r+1)*N/2) of every pointwise matrix (rows of the B image), all taps and all biases.
+template <int MODE>
+void pack_stack_pair_blob(uint8_t* b, int rank, const float* const* arrays, int first, const int (&widths)[4],
+                          const std::vector<int>& kmap1) {
+    using L = StackPairSmem<MODE>;
+    const int w_off[3] = {L::oPw1, L::oPw2, L::oPw3}, t_off[3] = {L::oTap1, L::oTap2, L::oTap3};
+    const int kpad[3] = {L::KP1, 128, 128}, nh[3] = {64, 64, 32}, b_off[3] = {0, 128, 256};
+    for (int l = 0; l < 3; ++l) {
+        const int i = first + 3 * l, cin = widths[l], cout = widths[l + 1];
+        const std::vector<int> km = l == 0 ? kmap1 : identity_map(cin);
+        for (int c = 0; c < cin; ++c)
+            for (int n = rank * nh[l]; n < (rank + 1) * nh[l] && n < cout; ++n) {
+                const int k = km[c], row = n - rank * nh[l];
+                *reinterpret_cast<__half*>(b + w_off[l] + size_t(k / 64) * nh[l] * 128 + sw128_offset(row, k % 64)) =
+                    __float2half(arrays[i + 1][size_t(c) * cout + n]);
+            }
+        __half* dw = reinterpret_cast<__half*>(b + t_off[l]);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int c = 0; c < cin; ++c) dw[tap * kpad[l] + km[c]] = __float2half(arrays[i][size_t(tap) * cin + c]);
+        float* bias = reinterpret_cast<float*>(b + L::oBias) + b_off[l];
+        for (int n = 0; n < cout; ++n) bias[n] = arrays[i + 2][n];
+    }
+}
+
 template <int MODE>
 int pack_stack_blob(uint8_t* b, const float* const* arrays, const int64_t* sizes, int first, const int (&widths)[4],
                     const std::vector<int>& kmap1) {
@@ -299,6 +328,8 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->readout_blob);
     cudaFree(e->stack_init_blob);
     for (auto* b : e->stack_upd_blobs) cudaFree(b);
+    cudaFree(e->pair_init_blob);
+    for (auto* b : e->pair_upd_blobs) cudaFree(b);
     cudaFree(e->nn_index);
     cudaFree(e->focc);
     cudaFree(e->pos_enc);
@@ -388,6 +419,15 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
         if (cudaMalloc(&e->stack_init_blob, host.size()) != cudaSuccess ||
             cudaMemcpy(e->stack_init_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading StateInit stack weights failed"));
+        using PI = StackPairSmem<kStackInit>;
+        std::vector<uint8_t> ph(size_t(PI::kBlob) * d.n_io * 2, 0);
+        for (int m = 0; m < d.n_io; ++m)
+            for (int r = 0; r < 2; ++r)
+                pack_stack_pair_blob<kStackInit>(ph.data() + (size_t(m) * 2 + r) * PI::kBlob, r, weight_arrays, 9 * m, widths_i,
+                                                 identity_map(widths_i[0]));
+        if (cudaMalloc(&e->pair_init_blob, ph.size()) != cudaSuccess ||
+            cudaMemcpy(e->pair_init_blob, ph.data(), ph.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(NRX_ERR_CUDA, "uploading StateInit pair weights failed"));
     }
 
     // ---- iterations -----------------------------------------------------------------------------
@@ -398,6 +438,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     e->upd_layers.resize(d.num_it);
     e->agg_blobs.resize(d.num_it, nullptr);
     e->stack_upd_blobs.resize(d.num_it, nullptr);
+    e->pair_upd_blobs.resize(d.num_it, nullptr);
     for (int it = 0; it < d.num_it; ++it) {
         if (weight_sizes[idx] != int64_t(d.d_s) * d.units_agg || weight_sizes[idx + 1] != d.units_agg ||
             weight_sizes[idx + 2] != int64_t(d.units_agg) * d.d_s || weight_sizes[idx + 3] != d.d_s)
@@ -426,6 +467,13 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             if (cudaMalloc(&e->stack_upd_blobs[it], sb.size()) != cudaSuccess ||
                 cudaMemcpy(e->stack_upd_blobs[it], sb.data(), sb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(NRX_ERR_CUDA, "uploading UpdateState stack weights failed"));
+            using PU = StackPairSmem<kStackUpdate>;
+            std::vector<uint8_t> pb(size_t(PU::kBlob) * 2, 0);
+            for (int r = 0; r < 2; ++r)
+                pack_stack_pair_blob<kStackUpdate>(pb.data() + size_t(r) * PU::kBlob, r, weight_arrays, idx, widths_u, upd_map);
+            if (cudaMalloc(&e->pair_upd_blobs[it], pb.size()) != cudaSuccess ||
+                cudaMemcpy(e->pair_upd_blobs[it], pb.data(), pb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(NRX_ERR_CUDA, "uploading UpdateState pair weights failed"));
         }
         e->upd_layers[it].resize(3);
         for (int l = 0; l < 3; ++l) {
@@ -530,6 +578,8 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_readout_kernel, kRoSmem));
     acc(set_smem(nrx_stack_kernel<kStackInit, false>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, false>, StackSmem<kStackUpdate>::kTotal));
+    acc(set_smem(nrx_stack_pair_kernel<kStackInit>, StackPairSmem<kStackInit>::kTotal));
+    acc(set_smem(nrx_stack_pair_kernel<kStackUpdate>, StackPairSmem<kStackUpdate>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
@@ -575,7 +625,7 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    if (fused < 0 || fused > 2) return fail(NRX_ERR_INVALID, "fused must be 0, 1 or 2");
+    if (fused < 0 || fused > 3) return fail(NRX_ERR_INVALID, "fused must be 0, 1, 2 or 3");
     e->fused = fused;
     return NRX_OK;
 }
@@ -685,6 +735,12 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
             // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
             const bool pair = U == 2 && e->fused == 2;
+            // plan 3: CTA-pair stack kernels (two users, one stack for both users of a slot)
+            const bool cta_pair = U == 2 && e->fused == 3;
+            StackParams kq = kp;                        // geometry of the pair launches: items = (slot, chunk)
+            kq.n_chunks = choose_chunks(bp, F, e->num_sms / 2);
+            kq.num_items = kq.n_chunks * bp;
+            const int pgrid = 2 * (kq.num_items < e->num_sms / 2 ? kq.num_items : e->num_sms / 2);
             __half* sp_cur = abuf;
             __half* sp_alt = reinterpret_cast<__half*>(ws + w.abuf2);
             kp.z0 = z0; kp.s_out = s_cur;
@@ -697,7 +753,11 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             {
                 Timed t(e, st, NRX_K_STACK_INIT);
                 if (pair) nrx_stack_kernel<kStackInit, true><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
-                else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+                else if (cta_pair && !io_index) {
+                    kq.z0 = kp.z0; kq.s_out = kp.s_out; kq.wblob = e->pair_init_blob; kq.stack_index = nullptr;
+                    kq.default_stack = llr_head; kq.active_tx = kp.active_tx; kq.pair_agg = 0; kq.sp_out = nullptr;
+                    nrx_stack_pair_kernel<kStackInit><<<pgrid, kStackThreads, StackPairSmem<kStackInit>::kTotal, st>>>(kq);
+                } else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
             kp.stack_index = nullptr;
             kp.default_stack = 0;
@@ -711,7 +771,11 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
                 {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
-                    else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+                    else if (cta_pair) {
+                        kq.a_in = kp.a_in; kq.s_in = kp.s_in; kq.s_out = kp.s_out; kq.wblob = e->pair_upd_blobs[it];
+                        kq.stack_index = nullptr; kq.default_stack = 0; kq.pair_agg = 0; kq.sp_out = nullptr;
+                        nrx_stack_pair_kernel<kStackUpdate><<<pgrid, kStackThreads, StackPairSmem<kStackUpdate>::kTotal, st>>>(kq);
+                    } else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                 }
                 __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
                 tmp = sp_cur; sp_cur = sp_alt; sp_alt = tmp;

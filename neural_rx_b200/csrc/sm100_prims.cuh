@@ -207,6 +207,79 @@ __device__ __forceinline__ void umma_gemm_k(uint32_t tmem_d, uint32_t a_base, ui
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2) — validated by tools/umma_pair_probe.cu:
+// one MMA of M = 256 spans both CTAs; each CTA supplies its own 128-row A tile (same smem offset
+// in both) and HALF of the B operand (rank r holds weight rows [r*N/2, (r+1)*N/2)); each CTA's
+// TMEM receives D for its 128 rows and all N columns.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cluster-wide address of a shared-memory location in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// bounded wait with cluster-scope acquire (pairs with remote arrives and multicast commits)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();
+    }
+}
+// executed by ONE full warp in EACH CTA of the pair (same warp id, same smem slot offset)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// issued by ONE thread of the leader CTA (rank 0)
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate)), "r"(0u)
+        : "memory");
+}
+// arrive on the barrier at this smem offset in every CTA of `cta_mask` when the pair's MMAs are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+// [256 x K] x [N x K]^T over the pair: a_base / b_base are the (identical) smem offsets in both CTAs
+__device__ __forceinline__ void umma_gemm_k_pair(uint32_t tmem_d, uint32_t a_base, uint32_t a_slab_bytes, uint32_t b_base,
+                                                 uint32_t b_slab_bytes, uint32_t K, uint32_t idesc) {
+    for (uint32_t k = 0; k < K; k += 16) {
+        const uint32_t slab = k / kSlabK, koff = (k % kSlabK) * 2;
+        umma_f16_pair(tmem_d, umma_smem_desc(a_base + slab * a_slab_bytes + koff),
+                      umma_smem_desc(b_base + slab * b_slab_bytes + koff), idesc, k > 0);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------

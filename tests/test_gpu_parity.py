@@ -99,12 +99,13 @@ def test_fused_equals_layerwise(label, n_prb, batch):
     if cfg.num_mcss_supported > 1:
         kw = dict(io_index=np.tile(np.array([[0, 1]], np.int32), (batch, 1)))
     outs = []
-    for fused in (1, 2, 0):
+    for fused in (1, 2, 0, 3):
         eng = _engine(cfg, weights, grid, fused=fused)
         outs.append(_run(eng, sb, **dict(kw)))
         eng.close()
     for k in ("llr", "llr_grid", "h_hat_refined"):
         assert rel_l2(outs[0][k], outs[2][k]) <= 1e-6, k      # fused stacks vs layer-per-kernel
+        assert rel_l2(outs[3][k], outs[2][k]) <= 1e-6, k      # CTA-pair stack kernels vs layer-per-kernel
         # the two-user fast path takes the other user's message directly instead of forming
         # (sp_0 + sp_1) - sp_u in fp32 (utils/neural_rx.py:196) and rounds sp (not a) to fp16:
         # same function, differences at fp16 round-off level
