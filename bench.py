@@ -148,20 +148,31 @@ def run_reference(args, rank):
 
 
 def latency_percentiles(eng, y1, act1, n: int = 200):
+    """Batch-1 latency of one forward (CUDA events around it): eager launches through the C ABI and
+    the same forward replayed from a CUDA graph (NrxEngine.capture)."""
     import torch
-    for _ in range(10):
-        eng.forward(y1, act1, want=("llr", "h_hat_refined"))
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(n):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.forward(y1, act1, want=("llr", "h_hat_refined"))
-        b.record()
-        b.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
-    ts = np.sort(np.asarray(ts))
-    return {"p50": float(ts[len(ts) // 2]), "p99": float(ts[min(len(ts) - 1, int(0.99 * len(ts)))]), "n": n}
+    want = ("llr", "h_hat_refined")
+
+    def measure(fn):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts = np.sort(np.asarray(ts))
+        return float(ts[len(ts) // 2]), float(ts[min(len(ts) - 1, int(0.99 * len(ts)))])
+
+    outs = {}
+    e50, e99 = measure(lambda: eng.forward(y1, act1, want=want, out=outs))
+    graph, _ = eng.capture(y1, act1, want=want)
+    g50, g99 = measure(graph.replay)
+    return {"p50": g50, "p99": g99, "eager_p50": e50, "eager_p99": e99, "n": n, "mode": "cuda graph replay"}
 
 
 def main():

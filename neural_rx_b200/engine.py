@@ -280,6 +280,27 @@ class NrxEngine:
         del per
         return res
 
+    # ---- CUDA-graph replay of a fixed-shape forward (latency mode) ---------------------------------
+    def capture(self, y, active_tx, io_index=None, head_index=None, llr_head: int = 0,
+                out_bits: Optional[int] = None, want: Sequence[str] = ("llr", "h_hat_refined", "h_hat")):
+        """Capture one forward on the given (static) input tensors into a CUDA graph.  nrx_forward
+        only enqueues kernels (no allocation, no synchronisation), so it can be recorded as is.
+        Returns ``(graph, outputs)``: overwrite ``y`` / ``active_tx`` in place, call ``graph.replay()``
+        and read ``outputs`` (same tensors every time)."""
+        import torch
+
+        outs: Dict = {}
+        kw = dict(io_index=io_index, head_index=head_index, llr_head=llr_head, out_bits=out_bits, want=want, out=outs)
+        side = torch.cuda.Stream(device=y.device)
+        side.wait_stream(torch.cuda.current_stream(y.device))
+        with torch.cuda.stream(side):
+            self.forward(y, active_tx, **kw)              # warm-up: allocates outputs and the workspace
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.forward(y, active_tx, **kw)
+        torch.cuda.current_stream(y.device).wait_stream(side)
+        return graph, {k: v for k, v in outs.items() if not k.startswith("_")}
+
     # ---- Aerial / TensorRT-shaped call (NeuralReceiverONNX.forward, utils/neural_rx.py:1773-1812) ----
     def set_aerial_dmrs(self, dmrs_ofdm_pos, dmrs_subcarrier_pos) -> None:
         op = np.ascontiguousarray(dmrs_ofdm_pos, dtype=np.int32)

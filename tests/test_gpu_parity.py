@@ -396,3 +396,25 @@ def test_aerial_shaped_entry(label, n_prb, batch):
     rx.num_it = 1
     with pytest.raises(AssertionError, match="Invalid number of iterations"):
         rx.num_it = cfg.num_nrx_iter + 1
+
+
+def test_cuda_graph_replay_matches_eager():
+    """nrx_forward is capturable (no allocation / synchronisation inside): a replayed graph gives
+    the same bits as the eager call, also after the static input has been overwritten."""
+    import torch
+    cfg = get_config("nrx_rt")
+    weights, _ = get_weights(cfg)
+    grid = build_grid(cfg, n_size_bwp=6)
+    sb = make_slots(cfg, grid, batch=2, ebno_db=6.0, seed=71)
+    eng = _engine(cfg, weights, grid)
+    y = torch.as_tensor(sb.y[:1]).cuda()
+    act = torch.as_tensor(sb.active_tx[:1]).cuda()
+    graph, outs = eng.capture(y, act, want=("llr", "h_hat_refined"))
+    for i in (1, 0):
+        y.copy_(torch.as_tensor(sb.y[i:i + 1]))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = outs["llr"].cpu().numpy().copy()
+        ref = eng.forward(torch.as_tensor(sb.y[i:i + 1]).cuda(), act, want=("llr",))["llr"].cpu().numpy()
+        assert np.array_equal(got, ref)
+    eng.close()
