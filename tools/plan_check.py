@@ -1,3 +1,6 @@
+"""Run every execution plan (nrx_set_fused 1, 2, 0, 3) in its own process on a few small cases and
+report success / the CUDA error per plan — a sticky device error in one plan cannot mask the others
+(compute-sanitizer is not available on the GPU pool).  usage: python tools/plan_check.py"""
 import os, sys, subprocess
 ROOT='/root/repo'
 code = r'''
@@ -19,6 +22,6 @@ print("OK", float(out["llr"].abs().mean()))
 ''' % ROOT
 open('gpurun_out/_one.py','w').write(code)
 for case in [("nrx_rt",4,3),("nrx_rt",1,2)]:
-    for mode in (1,2,0,3):
+    for mode in (1, 2, 0, 3):
         r = subprocess.run([sys.executable,'gpurun_out/_one.py',case[0],str(case[1]),str(case[2]),str(mode)],capture_output=True,text=True,env=dict(os.environ,CUDA_LAUNCH_BLOCKING="1"))
         print(case, mode, (r.stdout.strip().splitlines() or ['-'])[-1], '|', (r.stderr.strip().splitlines() or ['-'])[-1][:160])
