@@ -17,58 +17,8 @@
 
 using namespace nrx;
 
+// the pair primitives under test live in sm100_prims.cuh (shared with nrx_stack_pair.cuh)
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(99); } } while (0)
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory location in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(uint32_t(acc)), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask)
-                 : "memory");
-}
 
 // cluster of 2 CTAs x 128 threads.  A: [256][K] fp16 (rows 128*rank.. belong to CTA rank);
 // Bimg: per-CTA image [K/64 slabs][N/2 rows][128 B] (rank-major); D: [256][N] fp32
@@ -92,7 +42,7 @@ pair_kernel(const __half* __restrict__ A, const uint8_t* __restrict__ Bimg, floa
         mbar_init(&bar_mma, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc2(&tmem_slot, 256);
+    if (warp == 0) tmem_alloc_pair(&tmem_slot, 256);
     tc_fence_before_sync();
     cluster_sync_all();
     tc_fence_after_sync();
@@ -110,16 +60,11 @@ pair_kernel(const __half* __restrict__ A, const uint8_t* __restrict__ Bimg, floa
     mbar_wait(&bar_load, 0);
     __syncthreads();
     // both CTAs report "operands in place" to the LEADER's barrier
-    if (tid == 0) mbar_arrive_remote(mapa_shared(smem_u32(&bar_ready), 0));
+    if (tid == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bar_ready), 0));
     if (rank == 0 && tid == 0) {
         mbar_wait_cluster(&bar_ready, 0);
         tc_fence_after_sync();
-        const uint32_t idesc = umma_idesc_f16(256, N);
-        for (uint32_t k = 0; k < K; k += 16) {
-            const uint32_t slab = k / 64, koff = (k % 64) * 2;
-            umma_f16_pair(tbase, umma_smem_desc(smem_u32(sA) + slab * 128 * 128 + koff),
-                          umma_smem_desc(smem_u32(sB) + slab * NH * 128 + koff), idesc, k > 0);
-        }
+        umma_gemm_k_pair(tbase, smem_u32(sA), 128 * 128, smem_u32(sB), NH * 128, K, umma_idesc_f16(256, N));
         umma_commit_pair(&bar_mma, 0b11);
     }
     mbar_wait_cluster(&bar_mma, 0);
@@ -133,7 +78,7 @@ pair_kernel(const __half* __restrict__ A, const uint8_t* __restrict__ Bimg, floa
     }
     tc_fence_before_sync();
     cluster_sync_all();
-    if (warp == 0) tmem_dealloc2(tbase, 256);
+    if (warp == 0) tmem_dealloc_pair(tbase, 256);
 }
 
 static float h2f(__half h) { return __half2float(h); }
