@@ -84,12 +84,6 @@ struct StackSmem {
 __device__ __forceinline__ uint2 lds64(const void* p) { return *reinterpret_cast<const uint2*>(p); }
 __device__ __forceinline__ void sts64(void* p, uint2 v) { *reinterpret_cast<uint2*>(p) = v; }
 
-// fp32 pair -> fp16x2 with ReLU in one instruction (lo in the low half)
-__device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
 
 // Depthwise 3x3 of NFOUT consecutive subcarriers for two OFDM symbols (t0, t0+1) and four
 // channels.  Input rows (fi, t) live at  (fi < 2 ? carry : fresh - 2 rows) + (fi*14 + t)*RS  (the

@@ -283,6 +283,12 @@ __device__ __forceinline__ void umma_gemm_k_pair(uint32_t tmem_d, uint32_t a_bas
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
+// fp32 pair -> fp16x2 with ReLU in one instruction (lo in the low half)
+__device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
