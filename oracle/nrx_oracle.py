@@ -3,11 +3,19 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
 legs may import this module; the product (``neural_rx_b200``) never does.
 
-PARITY UNPINNED at LLR level: the reference ships no golden LLR vectors, no fixtures and no
-evaluation seeds, and its own implementation cannot run here (TensorFlow and
-Sionna are absent; the fork's torch port is broken).  This file is therefore a
-plain restatement of the *original TF semantics*, each function citing the reference lines it
-follows.  What *is* pinned against reference artefacts (tests/test_oracle_pins.py): weight-list
+PARITY: pinned block by block against the reference's own code, unpinned end to end.  The
+reference ships no golden LLR vectors, fixtures or seeds and cannot run end to end
+here (TensorFlow / Sionna absent, the fork's torch port is broken), but several of
+its classes are self-contained torch / NumPy code.  ``tests/golden/make_ref_fixtures.py`` executes
+them (extracted from the reference sources with ``ast``) on seeded inputs with the shipped weights
+and ``tests/test_oracle_pins.py`` checks this file against those outputs:
+``AggregateUserStates`` (utils/neural_rx.py:135-207), ``ReadoutLLRs`` / ``ReadoutChEst`` (:309-404),
+``NearestNeighborInterpolator`` (:919-1004), ``NRPreprocessing`` (:1614-1670) and the fork's
+``SeparableConv2d`` twin of Keras SeparableConv2D (utils/neural_rx copy_pytorch.py:34-51).  What
+those cannot pin — the composition of the blocks (concat orders, normalisation, residual, iteration
+loop: CGNN.forward :544-595 is defective in the fork), the LS/FOCC arithmetic of Sionna's estimator
+and the demapping order — is a plain restatement of the *original TF semantics*, each function citing
+the reference lines it follows.  Also pinned against reference artefacts: weight-list
 layout and parameter counts for every shipped ``weights/*_weights`` file
 (``notebooks/nrx_architecture.ipynb:257,295-308,382``), I/O shapes of the TensorRT bindings
 (``notebooks/real_time_nrx.ipynb`` cell 6/16), the PUSCH geometry dump
@@ -179,6 +187,24 @@ def dense(x, layer, relu: bool, emu: Emulation = EXACT):
     return torch.relu(o) if relu else o
 
 
+def mlp(x, layers, emu: Emulation = EXACT):
+    """Dense stack with ReLU on the hidden layers (ReadoutLLRs ``utils/neural_rx.py:309-355``,
+    ReadoutChEst ``:358-404``, the message MLP of AggregateUserStates ``:176-188``)."""
+    for l in layers[:-1]:
+        x = dense(x, l, True, emu)
+    return dense(x, layers[-1], False, emu)
+
+
+def aggregate_user_states(agg_layers, s, active_tx, emu: Emulation = EXACT):
+    """``AggregateUserStates.forward`` (``utils/neural_rx.py:176-207``): s [B,U,F,T,d_s],
+    active_tx [B,U] -> a [B,U,F,T,d_s] = (sum over the OTHER active users of MLP(s)) / max(n_active - 1, 1)."""
+    sp = mlp(s, agg_layers, emu) * active_tx[:, :, None, None, None]                  # :184-193
+    a = sp.sum(dim=1, keepdim=True) - sp                                              # :196
+    p = torch.relu(active_tx.sum(dim=1, keepdim=True) - 1.0)                          # :199-200
+    p = torch.where(p == 0.0, torch.ones_like(p), 1.0 / torch.clamp(p, min=1e-10))    # :203
+    return a * p[:, :, None, None, None]
+
+
 # --------------------------------------------------------------------------------------------
 # CGNN forward (utils/neural_rx.py:544-595; TF-faithful draft copy_pytorch.py:470-514)
 # --------------------------------------------------------------------------------------------
@@ -215,19 +241,10 @@ def cgnn_forward(net, arch: OracleArch, y, pe, h_hat, active_tx, mcs_ue_mask,
         s = s.reshape(B * U, *z0.shape[1:3], arch.d_s)
     s = emu.qs(s)
 
-    act = active_tx[:, :, None, None, None]
     for i in range(num_it):
         agg, upd = net["it"][i]
         # AggregateUserStates (:176-207)
-        sp = s
-        for l in agg[:-1]:
-            sp = dense(sp, l, True, emu)
-        sp = dense(sp, agg[-1], False, emu)
-        sp = sp.reshape(B, U, *sp.shape[1:]) * act
-        a = sp.sum(dim=1, keepdim=True) - sp
-        p = torch.relu(active_tx.sum(dim=1, keepdim=True) - 1.0)
-        p = torch.where(p == 0.0, torch.ones_like(p), 1.0 / torch.clamp(p, min=1e-10))
-        a = (a * p[:, :, None, None, None]).reshape(B * U, *sp.shape[2:])
+        a = aggregate_user_states(agg, s.reshape(B, U, *s.shape[1:]), active_tx, emu).reshape(B * U, *s.shape[1:])
         # UpdateState (:249-270): concat [a, s, pe], sep-conv stack, skip connection
         z = torch.cat([a, s, pet], dim=-1)
         s = emu.qs(s + run_stack(z, upd))
@@ -235,17 +252,11 @@ def cgnn_forward(net, arch: OracleArch, y, pe, h_hat, active_tx, mcs_ue_mask,
     llrs = []
     for m in range(len(arch.num_bits_per_symbol)):
         head = net["llr"][0] if arch.var_mcs_masking else net["llr"][m]
-        o = s
-        for l in head[:-1]:
-            o = dense(o, l, True, emu)
-        o = dense(o, head[-1], False, emu)
+        o = mlp(s, head, emu)
         if arch.var_mcs_masking:
             o = o[..., :arch.num_bits_per_symbol[m]]                          # :586-588
         llrs.append(o.reshape(B, U, *o.shape[1:]))
-    o = s
-    for l in net["chest"][:-1]:
-        o = dense(o, l, True, emu)
-    h_ref = dense(o, net["chest"][-1], False, emu)
+    h_ref = mlp(s, net["chest"], emu)
     return llrs, h_ref.reshape(B, U, *h_ref.shape[1:])
 
 

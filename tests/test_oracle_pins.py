@@ -212,3 +212,88 @@ def test_aerial_preprocessing_matches_documented_semantics():
     d = np.abs(h[:, 1] - r[:, 1]).max(axis=(0, 2, 3))
     assert list(np.flatnonzero(d > 0)) == [12, 24]
     assert np.abs(pe - grid.pos_enc).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# The oracle against the reference's OWN code, executed by tests/golden/make_ref_fixtures.py
+# (self-contained torch / NumPy classes extracted from the reference sources with ast)
+# ------------------------------------------------------------------------------------------------
+def _ref_fixtures():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_exec_fixtures.npz"))
+
+
+def _rt_net():
+    import torch
+    from neural_rx_b200.config import get_config
+    from neural_rx_b200.weights import load_weights
+    from tests.common import oracle_arch, weight_path
+    cfg = get_config("nrx_rt")
+    if weight_path("nrx_rt") is None:
+        pytest.skip("weights/nrx_rt_weights not staged")
+    arch = oracle_arch(cfg)
+    return O.bind_weights(arch, load_weights(cfg, weight_path("nrx_rt")).to_list(), torch.float32)
+
+
+def test_aggregation_matches_reference_class():
+    """oracle.aggregate_user_states == reference AggregateUserStates.forward (utils/neural_rx.py:135-207)
+    for 3 users and active masks [1,1,1], [1,0,1], [0,1,0], [0,0,0] (scaling 1/2, 1, p == 0 -> 1)."""
+    import torch
+    g, net = _ref_fixtures(), _rt_net()
+    a = O.aggregate_user_states(net["it"][0][0], torch.as_tensor(g["agg_s"]), torch.as_tensor(g["agg_active"]))
+    assert np.abs(a.numpy() - g["agg_a"]).max() <= 2e-5 * np.abs(g["agg_a"]).max()
+
+
+def test_readouts_match_reference_classes():
+    """oracle.mlp == reference ReadoutLLRs / ReadoutChEst (utils/neural_rx.py:309-404)."""
+    import torch
+    g, net = _ref_fixtures(), _rt_net()
+    s = torch.as_tensor(g["ro_s"])
+    assert np.abs(O.mlp(s, net["llr"][0]).numpy() - g["ro_llr"]).max() <= 2e-5 * np.abs(g["ro_llr"]).max()
+    assert np.abs(O.mlp(s, net["chest"]).numpy() - g["ro_h"]).max() <= 2e-5 * np.abs(g["ro_h"]).max()
+
+
+def test_sepconv_matches_reference_torch_twin():
+    """oracle.sepconv (Keras SeparableConv2D semantics, H = subcarriers, W = symbols) == the fork's
+    SeparableConv2d (utils/neural_rx copy_pytorch.py:34-51) with the Keras -> torch weight layout map."""
+    import torch
+    g, net = _ref_fixtures(), _rt_net()
+    y = O.sepconv(torch.as_tensor(g["sep_x"]), net["init"][0][0], relu=False)
+    assert np.abs(y.numpy() - g["sep_y"]).max() <= 2e-5 * np.abs(g["sep_y"]).max()
+
+
+def test_nn_gather_indices_match_reference_interpolator():
+    """Nearest-pilot gather indices: oracle.nn_gather_indices and the closed form in
+    neural_rx_b200.pusch == reference NearestNeighborInterpolator (utils/neural_rx.py:919-1004)."""
+    from neural_rx_b200.config import get_config
+    from neural_rx_b200.pusch import build_grid
+    g = _ref_fixtures()
+    grid = build_grid(get_config("nrx_rt"), n_size_bwp=int(g["nn_prb"]))
+    ref = g["nn_gather_ind"].reshape(grid.num_tx, -1)
+    assert np.array_equal(O.nn_gather_indices(grid.pilots, grid.pilot_mask), ref)
+    assert np.array_equal(grid.nn_index, ref)
+
+
+def test_aerial_preprocessing_matches_reference_class():
+    """FOCC removal and the per-PRB nearest-pilot template == reference NRPreprocessing
+    (utils/neural_rx.py:1620-1670).  The reference enumerates pilots subcarrier-major / symbol-minor;
+    its positional encoding divides by torch's UNBIASED std (a defect of the fork):
+    equal to the oracle's population-std version up to the factor sqrt((n-1)/n), n = 12*T."""
+    g = _ref_fixtures()
+    k_idx, j_idx, pe = O.aerial_nn_indices(g["aer_ofdm_pos"], g["aer_sc_pos"], 14)
+    n_sym = g["aer_ofdm_pos"].shape[1]
+    U = k_idx.shape[0]
+    # The fork builds the RE list with torch.meshgrid (default 'ij': subcarrier-major) but views the
+    # result as [T, 12] as the TF original did with tf.meshgrid ('xy'): undo that view to get the
+    # per-RE values back in (subcarrier, symbol) order before comparing.
+    ref_idx = g["aer_nn_idx"].reshape(U, 12, 14)
+    assert np.array_equal(k_idx * n_sym + j_idx, ref_idx)
+    ref_pe = np.transpose(g["aer_pe"][:, :12], (0, 2, 1, 3)).reshape(U, 12, 14, 2)
+    n = 12 * 14
+    assert np.abs(pe * np.sqrt((n - 1) / n) - ref_pe).max() <= 1e-5
+    assert np.abs(g["aer_pe"][:, :12] - g["aer_pe"][:, 12:]).max() == 0      # tiled over the PRBs
+    # FOCC removal: [B, 2N, U, n_p] in the reference, [B, n_p, U, 2N] in the oracle's input convention
+    h = np.transpose(g["focc_in"], (0, 3, 2, 1))
+    B, n_p, U, C = h.shape
+    hf = np.repeat(h.reshape(B, n_p // 2, 2, U, C).sum(axis=2, keepdims=True) / 2.0, 2, axis=2).reshape(B, n_p, U, C)
+    assert np.abs(np.transpose(hf, (0, 3, 2, 1)) - g["focc_out"]).max() <= 1e-6
