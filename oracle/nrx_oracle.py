@@ -10,7 +10,8 @@ its classes are self-contained torch / NumPy code.  ``tests/golden/make_ref_fixt
 them (extracted from the reference sources with ``ast``) on seeded inputs with the shipped weights
 and ``tests/test_oracle_pins.py`` checks this file against those outputs:
 ``AggregateUserStates`` (utils/neural_rx.py:135-207), ``ReadoutLLRs`` / ``ReadoutChEst`` (:309-404),
-``NearestNeighborInterpolator`` (:919-1004), ``NRPreprocessing`` (:1614-1670) and the fork's
+``NearestNeighborInterpolator`` (:919-1004), ``NRPreprocessing`` (:1614-1670), the NumPy
+positional-encoding pre-computation (utils/onnx_utils.py:203-247) and the fork's
 ``SeparableConv2d`` twin of Keras SeparableConv2D (utils/neural_rx copy_pytorch.py:34-51).  What
 those cannot pin — the composition of the blocks (concat orders, normalisation, residual, iteration
 loop: CGNN.forward :544-595 is defective in the fork), the LS/FOCC arithmetic of Sionna's estimator

@@ -13,6 +13,9 @@ inputs + outputs as fixtures; ``tests/test_oracle_pins.py`` then checks the orac
 * ``ReadoutLLRs`` / ``ReadoutChEst`` utils/neural_rx.py:309-404
 * ``NearestNeighborInterpolator``    utils/neural_rx.py:919-1004  (nearest-pilot gather indices of the LS estimator)
 * ``NRPreprocessing``                utils/neural_rx.py:1614-1700 (FOCC removal, per-PRB nearest-pilot template)
+* positional encoding                utils/onnx_utils.py:203-247  (the NumPy part of the pre-computation inside
+                                     ``NRXDataGenerator.__init__``: a code FRAGMENT, executed with the
+                                     pilot-position list the preceding TF lines would have produced)
 * ``SeparableConv2d``                utils/neural_rx copy_pytorch.py:34-51 (the torch twin of Keras
                                      SeparableConv2D the fork intended to use; that file is commented out,
                                      the class is un-commented on the fly)
@@ -135,6 +138,24 @@ def main():
         nn_idx, pe = quiet(pre._calculate_nn_indices, ofdm_pos, sc_pos, 14, 2)
     out.update(focc_in=h, focc_out=hf.numpy(), aer_ofdm_pos=ofdm_pos.numpy(), aer_sc_pos=sc_pos.numpy(),
                aer_nn_idx=nn_idx.numpy().astype(np.int32), aer_pe=pe.numpy().astype(np.float32))
+
+    # ---- positional encoding: NumPy fragment of utils/onnx_utils.py (distance to the nearest own pilot) ----
+    import textwrap
+    lines = open(os.path.join(REF, "utils", "onnx_utils.py")).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if "# Distance to the nearest pilot in time" in l)
+    i1 = next(i for i, l in enumerate(lines) if "nearest_pilot_dist = np.stack(" in l) + 3
+    frag = textwrap.dedent("\n".join(lines[i0:i1]))
+    grid4 = build_grid(cfg, n_size_bwp=4)
+    Tn, Fn = grid4.num_ofdm_symbols, grid4.num_subcarriers
+    ind = []                                   # what tf.where(|pilots_only| > 1e-3) yields, per tx: (t, f) row-major
+    for u in range(grid4.num_tx):
+        pu = np.zeros((Tn, Fn), np.complex64)
+        pu[grid4.pilot_mask] = grid4.pilots[u]
+        ind.append(np.argwhere(np.abs(pu) > 1e-3))
+    loc = {"np": np, "max_num_tx": grid4.num_tx, "rg": types.SimpleNamespace(num_ofdm_symbols=Tn, fft_size=Fn),
+           "pilot_ind_sorted": np.array(ind)}
+    exec(frag, loc)
+    out.update(pe_ref=np.transpose(loc["nearest_pilot_dist"], (0, 2, 1, 3)).astype(np.float32), pe_prb=np.int64(4))
 
     path = os.path.join(HERE, "ref_exec_fixtures.npz")
     np.savez_compressed(path, **out)

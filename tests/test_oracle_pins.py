@@ -297,3 +297,14 @@ def test_aerial_preprocessing_matches_reference_class():
     B, n_p, U, C = h.shape
     hf = np.repeat(h.reshape(B, n_p // 2, 2, U, C).sum(axis=2, keepdims=True) / 2.0, 2, axis=2).reshape(B, n_p, U, C)
     assert np.abs(np.transpose(hf, (0, 3, 2, 1)) - g["focc_out"]).max() <= 1e-6
+
+
+def test_positional_encoding_matches_reference_fragment():
+    """oracle.positional_encoding and neural_rx_b200.pusch == the NumPy pre-computation of
+    utils/onnx_utils.py:203-247 (nearest own pilot in time / frequency, zero mean, population std)."""
+    from neural_rx_b200.config import get_config
+    from neural_rx_b200.pusch import build_grid
+    g = _ref_fixtures()
+    grid = build_grid(get_config("nrx_rt"), n_size_bwp=int(g["pe_prb"]))
+    assert np.abs(O.positional_encoding(grid.pilots, grid.pilot_mask) - g["pe_ref"]).max() <= 1e-6
+    assert np.abs(grid.pos_enc - g["pe_ref"]).max() <= 1e-6
