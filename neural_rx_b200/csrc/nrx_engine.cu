@@ -18,6 +18,7 @@
 #include "nrx_kernels.cuh"
 #include "nrx_stack.cuh"
 #include "nrx_stack_pair.cuh"
+#include "nrx_stack_tm.cuh"
 
 using namespace nrx;
 
@@ -94,7 +95,10 @@ struct nrx_engine {
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
     uint8_t* pair_init_blob = nullptr;              // CTA-pair kernels: [n_io][2 ranks] half-weight images
     std::vector<uint8_t*> pair_upd_blobs;           // [it] -> [2 ranks]
-    int fused = 1;                                  // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
+    struct TmConsts { uint32_t tap[3][64][9]; float bias[320]; };
+    std::vector<TmConsts> tm_consts;                // [it] taps / biases of the TMEM-resident stack kernel (plan 4)
+    int fused = 1;                                  // 4: TMEM-resident UpdateState stacks (nrx_stack_tm.cuh);
+                                                    // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
                                                     // MLP in their tail (two users only), 3: CTA-pair stack kernels
                                                     // (experimental), 0: layer-per-kernel
     int32_t* nn_index = nullptr;
@@ -311,6 +315,54 @@ void launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, cons
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+using TensorMapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// [planes][F*14 rows][64] fp16 activation tensor, box = one subcarrier (14 rows x 128 B), 128-byte swizzle
+int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) {
+    const cuuint64_t dims[3] = {64, cuuint64_t(F) * kT, cuuint64_t(planes)};
+    const cuuint64_t strides[2] = {128, cuuint64_t(F) * kT * 128};
+    const cuuint32_t box[3] = {64, kT, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+}
+
+// plan 4: one TMEM-resident UpdateState stack launch
+int launch_stack_tm(nrx_engine* e, cudaStream_t st, int it, const __half* a_in, const __half* s_in, __half* s_out, int planes, int F) {
+    TmParams tp{};
+    int rc = make_plane_map(&tp.map_a, a_in, planes, F);
+    if (!rc) rc = make_plane_map(&tp.map_s, s_in, planes, F);
+    if (!rc) rc = make_plane_map(&tp.map_o, s_out, planes, F);
+    if (rc) return rc;
+    memcpy(tp.tap, e->tm_consts[it].tap, sizeof tp.tap);
+    memcpy(tp.bias, e->tm_consts[it].bias, sizeof tp.bias);
+    tp.wblob = e->stack_upd_blobs[it];
+    tp.F = F;
+    tp.jobs_per_plane = tm_choose_jobs(planes, F, e->num_sms);
+    tp.num_jobs = planes * tp.jobs_per_plane;
+    tp.num_items = (tp.num_jobs + kTmSeqs - 1) / kTmSeqs;
+    tp.steps_per_item = (F + tp.jobs_per_plane - 1) / tp.jobs_per_plane + kTmFill;
+    const int grid = tp.num_items < e->num_sms ? tp.num_items : e->num_sms;
+    Timed t(e, st, NRX_K_STACK_UPD);
+    nrx_stack_tm_kernel<<<grid, kTmThreads, TmSmem::kTotal, st>>>(tp);
+    return NRX_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -458,6 +510,15 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             std::vector<uint8_t> sb(LU::kBlob, 0);
             rc = pack_stack_blob<kStackUpdate>(sb.data(), weight_arrays, weight_sizes, idx, widths_u, upd_map);
             if (rc) return bail(rc);
+            {   // plan 4: the same taps as half2 per channel pair and the biases, passed as kernel parameters
+                nrx_engine::TmConsts tc{};
+                const int t_off[3] = {LU::oTap1, LU::oTap2, LU::oTap3};
+                for (int l = 0; l < 3; ++l)
+                    for (int c = 0; c < 64; ++c)
+                        for (int k = 0; k < 9; ++k) memcpy(&tc.tap[l][c][k], sb.data() + t_off[l] + (k * 128 + 2 * c) * 2, 4);
+                memcpy(tc.bias, sb.data() + LU::oBias, sizeof tc.bias);
+                e->tm_consts.push_back(tc);
+            }
             if (it + 1 < d.num_it) {     // message MLP of the next iteration (4 agg + 9 sep-conv arrays per iteration)
                 const int an = idx + 9;
                 if (weight_sizes[an] != int64_t(d.d_s) * d.units_agg || weight_sizes[an + 2] != int64_t(d.units_agg) * d.d_s)
@@ -582,6 +643,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_stack_pair_kernel<kStackUpdate>, StackPairSmem<kStackUpdate>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
+    acc(set_smem(nrx_stack_tm_kernel, TmSmem::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
     NRX_CUDA(cudaDeviceSynchronize());
     *out = e;
@@ -625,7 +687,8 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    if (fused < 0 || fused > 3) return fail(NRX_ERR_INVALID, "fused must be 0, 1, 2 or 3");
+    if (fused < 0 || fused > 4) return fail(NRX_ERR_INVALID, "fused must be 0 ... 4");
+    if (fused == 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plan 4 needs cuTensorMapEncodeTiled (driver entry point not found)");
     e->fused = fused;
     return NRX_OK;
 }
@@ -768,7 +831,10 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
                 kp.a_in = pair ? sp_cur : abuf; kp.s_in = s_cur; kp.s_out = s_alt;
                 kp.sp_out = pair && it + 1 < e->num_it ? sp_alt : nullptr;
                 kp.wblob = e->stack_upd_blobs[it];
-                {
+                if (e->fused == 4) {
+                    const int rc = launch_stack_tm(e, st, it, kp.a_in, kp.s_in, kp.s_out, BU, F);
+                    if (rc) return rc;
+                } else {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                     else if (cta_pair) {

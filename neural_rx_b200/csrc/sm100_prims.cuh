@@ -295,3 +295,70 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 }  // namespace nrx
+
+// ------------------------------------------------------------------------------------------
+// Additions for the TMEM-resident stack kernel (nrx_stack_tm.cuh): A operand of the MMA in tensor
+// memory (written by tcgen05.st from registers), tensor-map TMA with the 128-byte swizzle.
+// Validated by tools/umma_ts_probe.cu.
+// ------------------------------------------------------------------------------------------
+namespace nrx {
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// wait for the thread's outstanding tcgen05.ld; the registers are operands so that no use of them
+// can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+// thread `lane` of warp w writes 4 consecutive 32-bit columns of TMEM lane 32*(w%4)+lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is fp16 [128 lanes][K/2 columns], two consecutive K elements
+// per 32-bit column (even k in the low half); one instruction consumes K = 16 = 8 columns.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        : "memory");
+}
+__device__ __forceinline__ void umma_gemm_k_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_base, uint32_t b_slab_bytes,
+                                               uint32_t K, uint32_t idesc) {
+    for (uint32_t k = 0; k < K; k += 16) {
+        const uint32_t slab = k / kSlabK, koff = (k % kSlabK) * 2;
+        umma_f16_ts(tmem_d, tmem_a + k / 2, umma_smem_desc(b_base + slab * b_slab_bytes + koff), idesc, k > 0);
+    }
+}
+
+// 3-D tensor-map TMA (box lands in the map's swizzle pattern; out-of-range coordinates read zeros
+// and are clipped on stores)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
+}  // namespace nrx
