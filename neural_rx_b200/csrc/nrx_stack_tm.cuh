@@ -80,25 +80,41 @@ __device__ __forceinline__ TmSeq tm_seq_at(const TmParams& P, int n, int sigma) 
     return s;
 }
 
-// One channel pair of one input row: contribution to the three pending outputs.  pa = output row
-// r (completes: returned), pb = output row r+1; afterwards pa/pb are the pending sums of rows r+1/r+2.
-// Tap order and accumulation order are those of dw_slide (nrx_stack.cuh).
-__device__ __forceinline__ uint32_t tm_col(const TmParams& P, const int L, const int C, uint32_t x, uint32_t& pa, uint32_t& pb, int lane_l, int lane_r) {
-    const __half2 hx = u2h(x);
-    const __half2 hl = u2h(__shfl_sync(0xffffffffu, x, lane_l));
-    const __half2 hr = u2h(__shfl_sync(0xffffffffu, x, lane_r));
-    __half2 e = __hfma2(hl, u2h(P.tap[L][C][6]), u2h(pa));
-    e = __hfma2(hx, u2h(P.tap[L][C][7]), e);
-    e = __hfma2(hr, u2h(P.tap[L][C][8]), e);
-    __half2 a = __hfma2(hl, u2h(P.tap[L][C][3]), u2h(pb));
-    a = __hfma2(hx, u2h(P.tap[L][C][4]), a);
-    a = __hfma2(hr, u2h(P.tap[L][C][5]), a);
-    __half2 b = __hfma2(hl, u2h(P.tap[L][C][0]), __float2half2_rn(0.f));
-    b = __hfma2(hx, u2h(P.tap[L][C][1]), b);
-    b = __hfma2(hr, u2h(P.tap[L][C][2]), b);
-    pa = h2u(a);
-    pb = h2u(b);
-    return h2u(e);
+// Four channel pairs (one 16-byte chunk) of one input row: contribution to the three pending outputs
+// of each pair.  pa = output row r (completes: returned in o), pb = output row r+1; afterwards
+// pa/pb are the pending sums of rows r+1/r+2.  tp = taps of the chunk, [tap 0..8][pair 0..3].
+// Tap order and accumulation order per output are those of dw_slide (nrx_stack.cuh).
+__device__ __forceinline__ void tm_chunk(const uint32_t (&x)[4], uint32_t* pa, uint32_t* pb, const uint32_t* tp, int lane_l,
+                                         int lane_r, uint32_t (&o)[4]) {
+    __half2 hx[4], hl[4], hr[4], e[4], a[4], b[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        hx[w] = u2h(x[w]);
+        hl[w] = u2h(__shfl_sync(0xffffffffu, x[w], lane_l));
+        hr[w] = u2h(__shfl_sync(0xffffffffu, x[w], lane_r));
+        e[w] = u2h(pa[w]);
+        a[w] = u2h(pb[w]);
+        b[w] = __float2half2_rn(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int tap = k < 3 ? 6 + k : k < 6 ? k : k - 6;       // 6,7,8 (row r) | 3,4,5 (row r+1) | 0,1,2 (row r+2)
+        const uint4 tv = *reinterpret_cast<const uint4*>(tp + 4 * tap);
+        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const __half2 in = (tap % 3) == 0 ? hl[w] : (tap % 3) == 1 ? hx[w] : hr[w];
+            if (k < 3) e[w] = __hfma2(in, u2h(tw[w]), e[w]);
+            else if (k < 6) a[w] = __hfma2(in, u2h(tw[w]), a[w]);
+            else b[w] = __hfma2(in, u2h(tw[w]), b[w]);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        o[w] = h2u(e[w]);
+        pa[w] = h2u(a[w]);
+        pb[w] = h2u(b[w]);
+    }
 }
 
 __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __grid_constant__ TmParams P) {
@@ -111,6 +127,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     uint8_t* sOut = smem + S::oOut;
     __shared__ uint64_t bar_w, bar_afull[3], bar_dfull[3], bar_dempty[3], bar_z[4][kTmStages], bar_res[4];
     __shared__ uint32_t tmem_slot;
+    // taps [layer][chunk of 4 channel pairs][9][4] and biases: read by every lane at the same address (broadcast)
+    __shared__ __align__(16) uint32_t sTap[3 * 64 * 9];
+    __shared__ __align__(16) float sBias[320];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = warp >> 2, q = warp & 3;
@@ -132,6 +151,11 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         }
         fence_mbar_init();
     }
+    for (int i = tid; i < 3 * 64 * 9; i += kTmThreads) {     // [layer][chunk][tap][pair in chunk]
+        const int w = i & 3, k = (i >> 2) % 9, lc = i / 36;
+        sTap[i] = P.tap[lc >> 4][4 * (lc & 15) + w][k];
+    }
+    for (int i = tid; i < 320; i += kTmThreads) sBias[i] = P.bias[i];
     // rows 14 and 15 of every slot are never written by the TMA: the idle lanes read zeros there
     for (int i = tid; i < (S::kUsed - S::oZ) / 16; i += kTmThreads) st_shared_v4(smem + S::oZ + i * 16, make_uint4(0, 0, 0, 0));
     fence_proxy_async_smem();
@@ -147,6 +171,76 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
 
     const int n_my = int(blockIdx.x) < P.num_items ? (P.num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
     const int n_total = n_my * P.steps_per_item;
+    const int slot_off = q * (2 * kTmSlot) + h * kTmSlot;    // this sequence's slot inside sRes / sOut
+
+    // ---- role 0 only: input / residual fetch and the output epilogue -----------------------------
+    auto issue_z = [&](int m) {
+        if (t == 0) {
+            const TmSeq s = tm_seq_at(P, m, sigma);
+            const int fz = s.f0 - 3 + s.j;
+            const int st = m % kTmStages;
+            uint8_t* slot = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot);
+            mbar_arrive_expect_tx(&bar_z[q][st], 2 * kTmBoxBytes);
+            tma_load_3d(slot, &P.map_a, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
+            tma_load_3d(slot + kTmSlot, &P.map_s, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
+        }
+    };
+    auto issue_res = [&](int m) {
+        if (t == 0) {
+            const TmSeq s = tm_seq_at(P, m, sigma);
+            const int fo = s.f0 - kTmFill + s.j;
+            mbar_arrive_expect_tx(&bar_res[q], kTmBoxBytes);
+            tma_load_3d(sRes + slot_off, &P.map_s, 0, fo * kT, s.valid ? s.plane : -1, &bar_res[q]);
+        }
+    };
+    // bias + residual + fp16 + TMA store of output pass m (accumulator D3)
+    auto epilogue = [&](int m) {
+        const TmSeq s = tm_seq_at(P, m, sigma);
+        const int fo = s.f0 - kTmFill + s.j;
+        const bool ok = s.valid && s.j >= kTmFill && fo < s.f1;
+        mbar_wait(&bar_dfull[2], m & 1);
+        tc_fence_after_sync();
+        mbar_wait(&bar_res[q], m & 1);
+        if (t == 0) bulk_wait_read_all();              // the previous store has read the staging rows
+        __syncwarp();
+        const uint8_t* rs = sRes + slot_off + t * 128;
+        uint8_t* os = sOut + slot_off + t * 128;
+        const int swz = t & 7;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tlane + 256 + 16 * c4, v);
+            uint4 old[2];
+            old[0] = ld_shared_v4(rs + (((2 * c4) ^ swz) << 4));
+            old[1] = ld_shared_v4(rs + (((2 * c4 + 1) ^ swz) << 4));
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t ow[4] = {old[e].x, old[e].y, old[e].z, old[e].w};
+                const float4 b0 = *reinterpret_cast<const float4*>(sBias + 256 + 16 * c4 + 8 * e);
+                const float4 b1 = *reinterpret_cast<const float4*>(sBias + 256 + 16 * c4 + 8 * e + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 of = __half22float2(u2h(ow[i]));
+                    const float o0 = v[8 * e + 2 * i] + bb[2 * i];
+                    const float o1 = v[8 * e + 2 * i + 1] + bb[2 * i + 1];
+                    pk[i] = pack_half2(o0 + of.x, o1 + of.y);     // s <- s + update (:266)
+                }
+                st_shared_v4(os + (((2 * c4 + e) ^ swz) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            }
+        }
+        tc_fence_before_sync();                            // accumulator drained
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_dempty[2]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (t == 0) {
+            if (ok) tma_store_3d(&P.map_o, 0, fo * kT, s.plane, sOut + slot_off);
+            bulk_commit();
+        }
+    };
 
     // the elected lane of a layer's first warp: all four warps have stored their A rows and the
     // consumer has drained the previous accumulator -> issue the layer's GEMM
@@ -166,180 +260,91 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
 #pragma unroll
     for (int c = 0; c < 64; ++c) pa[c] = pb[c] = 0u;
 
+    // per-role constants of the common pass body (L = role: layer whose depthwise this warp runs)
+    const int L = role;
+    const uint32_t* tapL = sTap + L * (64 * 9);
+    const float* biasL = sBias + (L == 2 ? 128 : 0);        // bias of the layer that produced this warp's input
+    const uint32_t dsrc = tlane + (L == 2 ? 128u : 0u);    // accumulator this warp reads (role 0: values unused)
+    const uint32_t adst = tlane + 320u + 64u * uint32_t(L);
+    uint64_t* const bar_in = &bar_dfull[L == 0 ? 0 : L - 1];
+    uint64_t* const bar_in_empty = &bar_dempty[L == 0 ? 0 : L - 1];
+    const uint32_t m_lds = role == 0 ? 0xffffffffu : 0u;   // role 0 takes its input row from shared memory,
+    const int drain_lane = role == 0 ? 32 : 0;             // the others from the previous layer's accumulator
+    const int swz = t & 7;
+
     if (role == 0) {
-        // =====================================================================================
-        // layer 1 (input rows from shared memory) + output epilogue of layer 3
-        // =====================================================================================
-#pragma unroll
-        for (int c = 0; c < 16; ++c) tmem_st4(tlane + 320 + 4 * c, 0u, 0u, 0u, 0u);   // K padding columns of A1 stay zero
-        tmem_st_wait();
-        const int slot_off = q * (2 * kTmSlot) + h * kTmSlot;    // this sequence's slot inside sRes / sOut
-
-        auto issue_z = [&](int m) {
-            if (t == 0) {
-                const TmSeq s = tm_seq_at(P, m, sigma);
-                const int fz = s.f0 - 3 + s.j;
-                const int st = m % kTmStages;
-                uint8_t* slot = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot);
-                mbar_arrive_expect_tx(&bar_z[q][st], 2 * kTmBoxBytes);
-                tma_load_3d(slot, &P.map_a, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
-                tma_load_3d(slot + kTmSlot, &P.map_s, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
-            }
-        };
-        auto issue_res = [&](int m) {
-            if (t == 0) {
-                const TmSeq s = tm_seq_at(P, m, sigma);
-                const int fo = s.f0 - kTmFill + s.j;
-                mbar_arrive_expect_tx(&bar_res[q], kTmBoxBytes);
-                tma_load_3d(sRes + slot_off, &P.map_s, 0, fo * kT, s.valid ? s.plane : -1, &bar_res[q]);
-            }
-        };
-        // bias + residual + fp16 + TMA store of output pass m (accumulator D3)
-        auto epilogue = [&](int m) {
-            const TmSeq s = tm_seq_at(P, m, sigma);
-            const int fo = s.f0 - kTmFill + s.j;
-            const bool ok = s.valid && s.j >= kTmFill && fo < s.f1;
-            mbar_wait(&bar_dfull[2], m & 1);
-            tc_fence_after_sync();
-            mbar_wait(&bar_res[q], m & 1);
-            if (t == 0) bulk_wait_read_all();              // the previous store has read the staging rows
-            __syncwarp();
-            const uint8_t* rs = sRes + slot_off + t * 128;
-            uint8_t* os = sOut + slot_off + t * 128;
-            const int swz = t & 7;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float v[16];
-                tmem_ld16(tlane + 256 + 16 * c4, v);
-                uint4 old[2];
-                old[0] = ld_shared_v4(rs + (((2 * c4) ^ swz) << 4));
-                old[1] = ld_shared_v4(rs + (((2 * c4 + 1) ^ swz) << 4));
-                tmem_ld_wait();
-                if (c4 == 3) {                             // accumulator drained
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_dempty[2]);
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const uint32_t ow[4] = {old[e].x, old[e].y, old[e].z, old[e].w};
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 of = __half22float2(u2h(ow[i]));
-                        const int col = 16 * c4 + 8 * e + 2 * i;
-                        const float o0 = v[8 * e + 2 * i] + P.bias[256 + col];
-                        const float o1 = v[8 * e + 2 * i + 1] + P.bias[256 + col + 1];
-                        pk[i] = pack_half2(o0 + of.x, o1 + of.y);     // s <- s + update (:266)
-                    }
-                    st_shared_v4(os + (((2 * c4 + e) ^ swz) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (t == 0) {
-                if (ok) tma_store_3d(&P.map_o, 0, fo * kT, s.plane, sOut + slot_off);
-                bulk_commit();
-            }
-        };
-
         if (n_total > 0) issue_z(0);
         if (n_total > 1) issue_z(1);
-        mbar_wait(&bar_w, 0);
-        for (int n = 0; n < n_total + 3; ++n) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) tmem_st4(adst + 4 * c, 0u, 0u, 0u, 0u);
+        tmem_st_wait();
+    }
+    mbar_wait(&bar_w, 0);
+
+    // Every warp runs the SAME branch-free instruction stream for the pass body (three specialised
+    // bodies exceed the instruction cache): both input paths are executed and the role selects by
+    // masks; the role-dependent barriers sit outside the unrolled body.
+    const int n_end = role == 0 ? n_total + 3 : n_total;
+    for (int n = 0; n < n_end; ++n) {
+        const uint8_t* za = sZ + t * 128;
+        uint32_t m_acc = 0u;
+        uint64_t* wait_bar = bar_in;
+        uint32_t wait_parity = n & 1;
+        if (role == 0) {
             if (n >= 3) epilogue(n - 3);
             if (n >= 2 && n - 2 < n_total) issue_res(n - 2);
             if (n >= n_total) continue;
             if (n + 2 < n_total) issue_z(n + 2);
-            // ---- layer-1 pass n ----
             const int st = n % kTmStages;
-            mbar_wait(&bar_z[q][st], (n / kTmStages) & 1);
-            const uint8_t* za = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot) + t * 128;
-            const int swz = t & 7;
-#pragma unroll
-            for (int ch = 0; ch < 16; ++ch) {
-                if (ch == 7) continue;                     // channels 56..63 of `a` are padding
-                const uint8_t* src = (ch < 8 ? za : za + kTmSlot) + (((ch & 7) ^ swz) << 4);
-                const uint4 v = ld_shared_v4(src);
-                uint32_t o0, o1 = 0u, o2 = 0u, o3 = 0u;
-                o0 = tm_col(P, 0, 4 * ch, v.x, pa[4 * ch], pb[4 * ch], lane_l, lane_r);
-                if (ch != 15) {                            // channels 58..63 of `s | pe` are padding
-                    o1 = tm_col(P, 0, 4 * ch + 1, v.y, pa[4 * ch + 1], pb[4 * ch + 1], lane_l, lane_r);
-                    o2 = tm_col(P, 0, 4 * ch + 2, v.z, pa[4 * ch + 2], pb[4 * ch + 2], lane_l, lane_r);
-                    o3 = tm_col(P, 0, 4 * ch + 3, v.w, pa[4 * ch + 3], pb[4 * ch + 3], lane_l, lane_r);
-                }
-                if (ch == 0 && n >= 1) {                   // the previous GEMM has consumed A1
-                    mbar_wait(&bar_dfull[0], (n - 1) & 1);
-                    tc_fence_after_sync();
-                }
-                tmem_st4(tlane + 320 + 4 * ch, o0, o1, o2, o3);
-            }
-            tmem_st_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar_afull[0]);
-                if (q == 0) issue_mma(0, n);
-            }
-            __syncwarp();
+            wait_bar = &bar_z[q][st];
+            wait_parity = (n / kTmStages) & 1;
+            za = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot) + t * 128;
+        } else {
+            const TmSeq s = tm_seq_at(P, n, sigma);
+            const int f_in = s.f0 - 3 - L + s.j;           // layer 2 reads H1[f0-4+j], layer 3 reads H2[f0-5+j]
+            // rows outside the grid are the zero padding of the next layer; idle lanes hold zeros
+            m_acc = (t < kT && s.valid && f_in >= 0 && f_in < P.F) ? 0xffffffffu : 0u;
         }
-        if (t == 0) bulk_wait_all();
-    } else {
-        // =====================================================================================
-        // layers 2 and 3: input = previous layer's accumulator (bias + ReLU + fp16 in registers)
-        // =====================================================================================
-        auto run = [&](auto ltag) {
-            constexpr int L = decltype(ltag)::value;       // 1: consumes D1 -> A2, 2: consumes D2 -> A3
-            constexpr uint32_t dsrc = L == 1 ? 0u : 128u, adst = 320u + 64u * L;
-            constexpr int boff = L == 1 ? 0 : 128;
-            for (int n = 0; n < n_total; ++n) {
-                const TmSeq s = tm_seq_at(P, n, sigma);
-                const int f_in = s.f0 - 3 - L + s.j;
-                const uint32_t mask = (t < kT && s.valid && f_in >= 0 && f_in < P.F) ? 0xffffffffu : 0u;
-                mbar_wait(&bar_dfull[L - 1], n & 1);
-                tc_fence_after_sync();
-                uint32_t v[2][8];
-                tmem_ld8(tlane + dsrc, v[0]);
+        mbar_wait(wait_bar, wait_parity);
+        tc_fence_after_sync();
+        uint32_t v[2][8];
+        tmem_ld8(dsrc, v[0]);
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
-                    tmem_ld_wait8(v[ch & 1]);
-                    if (ch < 15) {
-                        tmem_ld8(tlane + dsrc + 8 * (ch + 1), v[(ch + 1) & 1]);
-                    } else {                               // accumulator drained
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_dempty[L - 1]);
-                    }
-                    uint32_t o[4];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const float v0 = __uint_as_float(v[ch & 1][2 * w]) + P.bias[boff + 8 * ch + 2 * w];
-                        const float v1 = __uint_as_float(v[ch & 1][2 * w + 1]) + P.bias[boff + 8 * ch + 2 * w + 1];
-                        const uint32_t x = pack_relu_half2(v0, v1) & mask;   // rows outside the grid are zero padding
-                        if (w == 0) o[0] = tm_col(P, L, 4 * ch + 0, x, pa[4 * ch + 0], pb[4 * ch + 0], lane_l, lane_r);
-                        if (w == 1) o[1] = tm_col(P, L, 4 * ch + 1, x, pa[4 * ch + 1], pb[4 * ch + 1], lane_l, lane_r);
-                        if (w == 2) o[2] = tm_col(P, L, 4 * ch + 2, x, pa[4 * ch + 2], pb[4 * ch + 2], lane_l, lane_r);
-                        if (w == 3) o[3] = tm_col(P, L, 4 * ch + 3, x, pa[4 * ch + 3], pb[4 * ch + 3], lane_l, lane_r);
-                    }
-                    if (ch == 0 && n >= 1) {               // the previous GEMM has consumed A_L
-                        mbar_wait(&bar_dfull[L], (n - 1) & 1);
-                        tc_fence_after_sync();
-                    }
-                    tmem_st4(tlane + adst + 4 * ch, o[0], o[1], o[2], o[3]);
-                }
-                tmem_st_wait();
+        for (int ch = 0; ch < 16; ++ch) {
+            const uint4 z = ld_shared_v4((ch < 8 ? za : za + kTmSlot) + (((ch & 7) ^ swz) << 4));
+            tmem_ld_wait8(v[ch & 1]);
+            if (ch < 15) {
+                tmem_ld8(dsrc + 8 * (ch + 1), v[(ch + 1) & 1]);
+            } else {                                       // accumulator drained
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&bar_afull[L]);
-                    if (q == 0) issue_mma(L, n);
-                }
-                __syncwarp();
+                if (lane == drain_lane) mbar_arrive(bar_in_empty);
             }
-        };
-        if (role == 1) run(std::integral_constant<int, 1>{});
-        else run(std::integral_constant<int, 2>{});
+            const float4 b0 = *reinterpret_cast<const float4*>(biasL + 8 * ch);
+            const float4 b1 = *reinterpret_cast<const float4*>(biasL + 8 * ch + 4);
+            uint32_t xw[4];                                // bias + ReLU + fp16 | input row from shared memory
+            xw[0] = (pack_relu_half2(__uint_as_float(v[ch & 1][0]) + b0.x, __uint_as_float(v[ch & 1][1]) + b0.y) & m_acc) | (z.x & m_lds);
+            xw[1] = (pack_relu_half2(__uint_as_float(v[ch & 1][2]) + b0.z, __uint_as_float(v[ch & 1][3]) + b0.w) & m_acc) | (z.y & m_lds);
+            xw[2] = (pack_relu_half2(__uint_as_float(v[ch & 1][4]) + b1.x, __uint_as_float(v[ch & 1][5]) + b1.y) & m_acc) | (z.z & m_lds);
+            xw[3] = (pack_relu_half2(__uint_as_float(v[ch & 1][6]) + b1.z, __uint_as_float(v[ch & 1][7]) + b1.w) & m_acc) | (z.w & m_lds);
+            uint32_t o[4];
+            tm_chunk(xw, pa + 4 * ch, pb + 4 * ch, tapL + ch * 36, lane_l, lane_r, o);
+            if (ch == 0 && n >= 1) {                       // the previous GEMM has consumed this layer's A tile
+                mbar_wait(&bar_dfull[L], (n - 1) & 1);
+                tc_fence_after_sync();
+            }
+            tmem_st4(adst + 4 * ch, o[0], o[1], o[2], o[3]);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&bar_afull[L]);
+            if (q == 0) issue_mma(L, n);
+        }
+        __syncwarp();
     }
+    if (role == 0 && t == 0) bulk_wait_all();
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);

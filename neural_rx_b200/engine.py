@@ -62,7 +62,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("NRX_B200_LIB") or _LIB_PATH      # env override: experiment builds only
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: build the CUDA library first (python -m neural_rx_b200.build). "
