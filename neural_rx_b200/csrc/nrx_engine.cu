@@ -97,6 +97,7 @@ struct nrx_engine {
     std::vector<uint8_t*> pair_upd_blobs;           // [it] -> [2 ranks]
     struct TmConsts { uint32_t tap[3][64][9]; float bias[320]; };
     std::vector<TmConsts> tm_consts;                // [it] taps / biases of the TMEM-resident stack kernel (plan 4)
+    std::vector<uint8_t*> tm_blobs;                 // [it] its pointwise B images (output channels in fragment order)
     int fused = 1;                                  // 4: TMEM-resident UpdateState stacks (nrx_stack_tm.cuh);
                                                     // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
                                                     // MLP in their tail (two users only), 3: CTA-pair stack kernels
@@ -351,7 +352,7 @@ int launch_stack_tm(nrx_engine* e, cudaStream_t st, int it, const __half* a_in, 
     if (rc) return rc;
     memcpy(tp.tap, e->tm_consts[it].tap, sizeof tp.tap);
     memcpy(tp.bias, e->tm_consts[it].bias, sizeof tp.bias);
-    tp.wblob = e->stack_upd_blobs[it];
+    tp.wblob = e->tm_blobs[it];
     tp.F = F;
     tp.jobs_per_plane = tm_choose_jobs(planes, F, e->num_sms);
     tp.num_jobs = planes * tp.jobs_per_plane;
@@ -380,6 +381,7 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->readout_blob);
     cudaFree(e->stack_init_blob);
     for (auto* b : e->stack_upd_blobs) cudaFree(b);
+    for (auto* b : e->tm_blobs) cudaFree(b);
     cudaFree(e->pair_init_blob);
     for (auto* b : e->pair_upd_blobs) cudaFree(b);
     cudaFree(e->nn_index);
@@ -516,8 +518,28 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                 for (int l = 0; l < 3; ++l)
                     for (int c = 0; c < 64; ++c)
                         for (int k = 0; k < 9; ++k) memcpy(&tc.tap[l][c][k], sb.data() + t_off[l] + (k * 128 + 2 * c) * 2, 4);
-                memcpy(tc.bias, sb.data() + LU::oBias, sizeof tc.bias);
+                const float* b_in = reinterpret_cast<const float*>(sb.data() + LU::oBias);
+                const int b_off[3] = {0, 128, 256}, n_pad[3] = {128, 128, 64};
+                for (int l = 0; l < 3; ++l)                // biases and B-image rows in the fragment's column order
+                    for (int n = 0; n < n_pad[l]; ++n) tc.bias[b_off[l] + tm_phys_col(n)] = b_in[b_off[l] + n];
                 e->tm_consts.push_back(tc);
+                std::vector<uint8_t> tb(TmSmem::kW, 0);
+                const int w_off[3] = {0, 32768, 65536};
+                for (int l = 0; l < 3; ++l) {
+                    const int cin = widths_u[l], cout = widths_u[l + 1];
+                    const float* w = weight_arrays[idx + 3 * l + 1];
+                    for (int c = 0; c < cin; ++c)
+                        for (int n = 0; n < cout; ++n) {
+                            const int k = l == 0 ? upd_map[c] : c;
+                            *reinterpret_cast<__half*>(tb.data() + w_off[l] + size_t(k / 64) * n_pad[l] * 128 +
+                                                       sw128_offset(tm_phys_col(n), k % 64)) = __float2half(w[size_t(c) * cout + n]);
+                        }
+                }
+                uint8_t* dev = nullptr;
+                if (cudaMalloc(&dev, tb.size()) != cudaSuccess ||
+                    cudaMemcpy(dev, tb.data(), tb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+                    return bail(fail(NRX_ERR_CUDA, "uploading plan-4 stack weights failed"));
+                e->tm_blobs.push_back(dev);
             }
             if (it + 1 < d.num_it) {     // message MLP of the next iteration (4 agg + 9 sep-conv arrays per iteration)
                 const int an = idx + 9;

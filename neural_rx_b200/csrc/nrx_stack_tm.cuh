@@ -80,41 +80,69 @@ __device__ __forceinline__ TmSeq tm_seq_at(const TmParams& P, int n, int sigma) 
     return s;
 }
 
-// Four channel pairs (one 16-byte chunk) of one input row: contribution to the three pending outputs
-// of each pair.  pa = output row r (completes: returned in o), pb = output row r+1; afterwards
-// pa/pb are the pending sums of rows r+1/r+2.  tp = taps of the chunk, [tap 0..8][pair 0..3].
-// Tap order and accumulation order per output are those of dw_slide (nrx_stack.cuh).
-__device__ __forceinline__ void tm_chunk(const uint32_t (&x)[4], uint32_t* pa, uint32_t* pb, const uint32_t* tp, int lane_l,
-                                         int lane_r, uint32_t (&o)[4]) {
-    __half2 hx[4], hl[4], hr[4], e[4], a[4], b[4];
+// Channel order.  A thread of the 16x256b fragment owns, per 16-column group c of an accumulator,
+// the columns 16c + 8e + 2g + d (e, d in {0,1}; g = T%4).  The pointwise weight images and biases of
+// plan 4 store output channel  16c + 4g + 2e + d  in that physical column (tm_phys_col), so the
+// four values a thread holds are four CONSECUTIVE channels = the A-operand columns 8c + 2g + e it
+// may write with the same fragment shape: every layer keeps the natural K order.
+__host__ __device__ constexpr int tm_phys_col(int n) { return (n & ~15) | ((n & 2) << 2) | ((n >> 1) & 6) | (n & 1); }
+
+// Two channel pairs (e = 0, 1) x two symbols (px) x two sequences (h) of one input row: contribution to
+// the three pending outputs of each.  pa = output row r (completes: returned in o), pb = output row
+// r+1; afterwards pa/pb are the pending sums of rows r+1/r+2.  tp = the thread's taps of the
+// chunk, [tap 0..8][g][e] (tp already points at g).  A thread's symbols are adjacent (2i, 2i+1): only
+// the outer neighbours come from other lanes (pair i-1 / i+1 = lane T-4 / T+4).  Tap order and
+// accumulation order per output are those of dw_slide (nrx_stack.cuh).
+__device__ __forceinline__ void tm_chunk(const uint32_t (&x)[8], uint32_t* pa, uint32_t* pb, const uint32_t* tp, int lane_l,
+                                         int lane_r, uint32_t (&o)[8]) {
+    // index = (h * 2 + px) * 2 + e
+    __half2 in[3][8], e[8], a[8], b[8];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        hx[w] = u2h(x[w]);
-        hl[w] = u2h(__shfl_sync(0xffffffffu, x[w], lane_l));
-        hr[w] = u2h(__shfl_sync(0xffffffffu, x[w], lane_r));
-        e[w] = u2h(pa[w]);
-        a[w] = u2h(pb[w]);
-        b[w] = __float2half2_rn(0.f);
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int ee = 0; ee < 2; ++ee) {
+            const int i0 = (h * 2 + 0) * 2 + ee, i1 = (h * 2 + 1) * 2 + ee;
+            const __half2 x0 = u2h(x[i0]), x1 = u2h(x[i1]);
+            in[0][i0] = u2h(__shfl_sync(0xffffffffu, x[i1], lane_l));    // symbol 2i-1
+            in[1][i0] = x0;
+            in[2][i0] = x1;
+            in[0][i1] = x0;
+            in[1][i1] = x1;
+            in[2][i1] = u2h(__shfl_sync(0xffffffffu, x[i0], lane_r));    // symbol 2i+2
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        e[i] = u2h(pa[i]);
+        a[i] = u2h(pb[i]);
+        b[i] = __float2half2_rn(0.f);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const int tap = k < 3 ? 6 + k : k < 6 ? k : k - 6;       // 6,7,8 (row r) | 3,4,5 (row r+1) | 0,1,2 (row r+2)
-        const uint4 tv = *reinterpret_cast<const uint4*>(tp + 4 * tap);
-        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+        const uint2 tv = *reinterpret_cast<const uint2*>(tp + 8 * tap);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const __half2 in = (tap % 3) == 0 ? hl[w] : (tap % 3) == 1 ? hx[w] : hr[w];
-            if (k < 3) e[w] = __hfma2(in, u2h(tw[w]), e[w]);
-            else if (k < 6) a[w] = __hfma2(in, u2h(tw[w]), a[w]);
-            else b[w] = __hfma2(in, u2h(tw[w]), b[w]);
+        for (int i = 0; i < 8; ++i) {
+            const __half2 w = u2h((i & 1) ? tv.y : tv.x);
+            if (k < 3) e[i] = __hfma2(in[tap % 3][i], w, e[i]);
+            else if (k < 6) a[i] = __hfma2(in[tap % 3][i], w, a[i]);
+            else b[i] = __hfma2(in[tap % 3][i], w, b[i]);
         }
     }
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        o[w] = h2u(e[w]);
-        pa[w] = h2u(a[w]);
-        pb[w] = h2u(b[w]);
+    for (int i = 0; i < 8; ++i) {
+        o[i] = h2u(e[i]);
+        pa[i] = h2u(a[i]);
+        pb[i] = h2u(b[i]);
     }
+}
+
+// predicated 8-byte shared-memory load (role 0 only reads the input rows)
+__device__ __forceinline__ uint2 lds64_if(const void* p, uint32_t pred) {
+    uint2 z = make_uint2(0u, 0u);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.shared.v2.b32 {%0, %1}, [%2];\n\t}"
+                 : "+r"(z.x), "+r"(z.y)
+                 : "r"(smem_u32(p)), "r"(pred));
+    return z;
 }
 
 __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __grid_constant__ TmParams P) {
@@ -127,15 +155,14 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     uint8_t* sOut = smem + S::oOut;
     __shared__ uint64_t bar_w, bar_afull[3], bar_dfull[3], bar_dempty[3], bar_z[4][kTmStages], bar_res[4];
     __shared__ uint32_t tmem_slot;
-    // taps [layer][chunk of 4 channel pairs][9][4] and biases: read by every lane at the same address (broadcast)
+    // taps [layer][chunk of 8 channel pairs][tap][g][e] and biases (physical column order)
     __shared__ __align__(16) uint32_t sTap[3 * 64 * 9];
     __shared__ __align__(16) float sBias[320];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = warp >> 2, q = warp & 3;
-    const int h = lane >> 4, t = lane & 15;
-    const int sigma = 2 * q + h;
-    const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+    const int pi = lane >> 2, g = lane & 3;                // symbol pair (2 pi, 2 pi + 1; pair 7 idle), column group
+    const int lane_l = (lane + 28) & 31, lane_r = (lane + 4) & 31;
 
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
@@ -151,19 +178,19 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         }
         fence_mbar_init();
     }
-    for (int i = tid; i < 3 * 64 * 9; i += kTmThreads) {     // [layer][chunk][tap][pair in chunk]
-        const int w = i & 3, k = (i >> 2) % 9, lc = i / 36;
-        sTap[i] = P.tap[lc >> 4][4 * (lc & 15) + w][k];
+    for (int i = tid; i < 3 * 64 * 9; i += kTmThreads) {     // [layer][chunk][tap][g][e] <- tap[layer][8 c + 2 g + e][tap]
+        const int ge = i & 7, k = (i >> 3) % 9, lc = i / 72;
+        sTap[i] = P.tap[lc >> 3][8 * (lc & 7) + ge][k];
     }
     for (int i = tid; i < 320; i += kTmThreads) sBias[i] = P.bias[i];
-    // rows 14 and 15 of every slot are never written by the TMA: the idle lanes read zeros there
+    // rows 14 and 15 of every slot are never written by the TMA: the idle symbol pair reads zeros there
     for (int i = tid; i < (S::kUsed - S::oZ) / 16; i += kTmThreads) st_shared_v4(smem + S::oZ + i * 16, make_uint4(0, 0, 0, 0));
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = tmem_slot;
-    const uint32_t tlane = tbase + (uint32_t(32 * q) << 16);
+    const uint32_t tlane = tbase + (uint32_t(32 * q) << 16);         // + (16 h << 16) for the second sequence
     if (tid == 0) {
         mbar_arrive_expect_tx(&bar_w, S::kW);
         bulk_g2s(sW, P.wblob, S::kW, &bar_w);
@@ -171,73 +198,72 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
 
     const int n_my = int(blockIdx.x) < P.num_items ? (P.num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
     const int n_total = n_my * P.steps_per_item;
-    const int slot_off = q * (2 * kTmSlot) + h * kTmSlot;    // this sequence's slot inside sRes / sOut
+    // byte offsets of this thread's two symbols / four channels inside a 14 x 128 B box (128-byte swizzle):
+    // channels 16 c + 4 g + {0..3}  ->  16-byte chunk 2 c + g/2, half g%2
+    const int row0 = (2 * pi) * 128, row1 = (2 * pi + 1) * 128;
+    const int sw0 = (2 * pi) & 7, sw1 = (2 * pi + 1) & 7;
+    auto box_off = [&](int px, int c) {
+        return (px ? row1 : row0) + ((((2 * c) + (g >> 1)) ^ (px ? sw1 : sw0)) << 4) + ((g & 1) << 3);
+    };
 
-    // ---- role 0 only: input / residual fetch and the output epilogue -----------------------------
+    // ---- role 0 only: input / residual fetch and the output epilogue (lanes 0 and 1 drive the TMA
+    //      of the warp's two sequences) -------------------------------------------------------------
     auto issue_z = [&](int m) {
-        if (t == 0) {
-            const TmSeq s = tm_seq_at(P, m, sigma);
+        if (lane < 2) {
+            const TmSeq s = tm_seq_at(P, m, 2 * q + lane);
             const int fz = s.f0 - 3 + s.j;
             const int st = m % kTmStages;
-            uint8_t* slot = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot);
+            uint8_t* slot = sZ + st * S::kStage + q * (4 * kTmSlot) + lane * (2 * kTmSlot);
             mbar_arrive_expect_tx(&bar_z[q][st], 2 * kTmBoxBytes);
             tma_load_3d(slot, &P.map_a, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
             tma_load_3d(slot + kTmSlot, &P.map_s, 0, fz * kT, s.valid ? s.plane : -1, &bar_z[q][st]);
         }
     };
     auto issue_res = [&](int m) {
-        if (t == 0) {
-            const TmSeq s = tm_seq_at(P, m, sigma);
+        if (lane < 2) {
+            const TmSeq s = tm_seq_at(P, m, 2 * q + lane);
             const int fo = s.f0 - kTmFill + s.j;
             mbar_arrive_expect_tx(&bar_res[q], kTmBoxBytes);
-            tma_load_3d(sRes + slot_off, &P.map_s, 0, fo * kT, s.valid ? s.plane : -1, &bar_res[q]);
+            tma_load_3d(sRes + q * (2 * kTmSlot) + lane * kTmSlot, &P.map_s, 0, fo * kT, s.valid ? s.plane : -1, &bar_res[q]);
         }
     };
     // bias + residual + fp16 + TMA store of output pass m (accumulator D3)
     auto epilogue = [&](int m) {
-        const TmSeq s = tm_seq_at(P, m, sigma);
-        const int fo = s.f0 - kTmFill + s.j;
-        const bool ok = s.valid && s.j >= kTmFill && fo < s.f1;
-        mbar_wait(&bar_dfull[2], m & 1);
+        mbar_wait_sleep(&bar_dfull[2], m & 1);
         tc_fence_after_sync();
-        mbar_wait(&bar_res[q], m & 1);
-        if (t == 0) bulk_wait_read_all();              // the previous store has read the staging rows
+        mbar_wait_sleep(&bar_res[q], m & 1);
+        if (lane < 2) bulk_wait_read_all();            // the previous store has read the staging rows
         __syncwarp();
-        const uint8_t* rs = sRes + slot_off + t * 128;
-        uint8_t* os = sOut + slot_off + t * 128;
-        const int swz = t & 7;
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-            float v[16];
-            tmem_ld16(tlane + 256 + 16 * c4, v);
-            uint4 old[2];
-            old[0] = ld_shared_v4(rs + (((2 * c4) ^ swz) << 4));
-            old[1] = ld_shared_v4(rs + (((2 * c4 + 1) ^ swz) << 4));
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const uint32_t ow[4] = {old[e].x, old[e].y, old[e].z, old[e].w};
-                const float4 b0 = *reinterpret_cast<const float4*>(sBias + 256 + 16 * c4 + 8 * e);
-                const float4 b1 = *reinterpret_cast<const float4*>(sBias + 256 + 16 * c4 + 8 * e + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 of = __half22float2(u2h(ow[i]));
-                    const float o0 = v[8 * e + 2 * i] + bb[2 * i];
-                    const float o1 = v[8 * e + 2 * i + 1] + bb[2 * i + 1];
-                    pk[i] = pack_half2(o0 + of.x, o1 + of.y);     // s <- s + update (:266)
-                }
-                st_shared_v4(os + (((2 * c4 + e) ^ swz) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-            }
+        for (int hc = 0; hc < 8; ++hc) {
+            const int h = hc >> 2, c = hc & 3;
+            uint32_t r[8], dummy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            tmem_ld_16x256b_x2(tlane + (uint32_t(16 * h) << 16) + 256 + 16 * c, r);
+            const uint8_t* rs = sRes + q * (2 * kTmSlot) + h * kTmSlot;
+            uint8_t* os = sOut + q * (2 * kTmSlot) + h * kTmSlot;
+            const float2 bA = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 2 * g);
+            const float2 bB = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 8 + 2 * g);
+            const uint2 old0 = lds64(rs + box_off(0, c)), old1 = lds64(rs + box_off(1, c));
+            tmem_ld_wait16(r, dummy);
+            const float2 o00 = __half22float2(u2h(old0.x)), o01 = __half22float2(u2h(old0.y));
+            const float2 o10 = __half22float2(u2h(old1.x)), o11 = __half22float2(u2h(old1.y));
+            uint2 w0, w1;                              // s <- s + update (:266)
+            w0.x = pack_half2((__uint_as_float(r[0]) + bA.x) + o00.x, (__uint_as_float(r[1]) + bA.y) + o00.y);
+            w0.y = pack_half2((__uint_as_float(r[4]) + bB.x) + o01.x, (__uint_as_float(r[5]) + bB.y) + o01.y);
+            w1.x = pack_half2((__uint_as_float(r[2]) + bA.x) + o10.x, (__uint_as_float(r[3]) + bA.y) + o10.y);
+            w1.y = pack_half2((__uint_as_float(r[6]) + bB.x) + o11.x, (__uint_as_float(r[7]) + bB.y) + o11.y);
+            sts64(os + box_off(0, c), w0);
+            sts64(os + box_off(1, c), w1);
         }
         tc_fence_before_sync();                            // accumulator drained
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_dempty[2]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (t == 0) {
-            if (ok) tma_store_3d(&P.map_o, 0, fo * kT, s.plane, sOut + slot_off);
+        if (lane < 2) {
+            const TmSeq s = tm_seq_at(P, m, 2 * q + lane);
+            const int fo = s.f0 - kTmFill + s.j;
+            if (s.valid && s.j >= kTmFill && fo < s.f1) tma_store_3d(&P.map_o, 0, fo * kT, s.plane, sOut + q * (2 * kTmSlot) + lane * kTmSlot);
             bulk_commit();
         }
     };
@@ -256,38 +282,34 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         umma_commit(&bar_dfull[L]);
     };
 
-    uint32_t pa[64], pb[64];
+    uint32_t pa[64], pb[64];                               // [chunk 8][h 2][px 2][e 2]
 #pragma unroll
     for (int c = 0; c < 64; ++c) pa[c] = pb[c] = 0u;
 
     // per-role constants of the common pass body (L = role: layer whose depthwise this warp runs)
     const int L = role;
-    const uint32_t* tapL = sTap + L * (64 * 9);
-    const float* biasL = sBias + (L == 2 ? 128 : 0);        // bias of the layer that produced this warp's input
+    const uint32_t* tapL = sTap + L * (64 * 9) + 2 * g;
+    const float* biasL = sBias + (L == 2 ? 128 : 0) + 2 * g;   // bias of the layer that produced this warp's input
     const uint32_t dsrc = tlane + (L == 2 ? 128u : 0u);    // accumulator this warp reads (role 0: values unused)
     const uint32_t adst = tlane + 320u + 64u * uint32_t(L);
     uint64_t* const bar_in = &bar_dfull[L == 0 ? 0 : L - 1];
     uint64_t* const bar_in_empty = &bar_dempty[L == 0 ? 0 : L - 1];
-    const uint32_t m_lds = role == 0 ? 0xffffffffu : 0u;   // role 0 takes its input row from shared memory,
+    const uint32_t m_lds = role == 0 ? 1u : 0u;            // role 0 takes its input row from shared memory,
     const int drain_lane = role == 0 ? 32 : 0;             // the others from the previous layer's accumulator
-    const int swz = t & 7;
 
     if (role == 0) {
         if (n_total > 0) issue_z(0);
         if (n_total > 1) issue_z(1);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) tmem_st4(adst + 4 * c, 0u, 0u, 0u, 0u);
-        tmem_st_wait();
     }
     mbar_wait(&bar_w, 0);
 
     // Every warp runs the SAME branch-free instruction stream for the pass body (three specialised
     // bodies exceed the instruction cache): both input paths are executed and the role selects by
-    // masks; the role-dependent barriers sit outside the unrolled body.
+    // masks / predicates; the role-dependent barriers sit outside the unrolled body.
     const int n_end = role == 0 ? n_total + 3 : n_total;
     for (int n = 0; n < n_end; ++n) {
-        const uint8_t* za = sZ + t * 128;
-        uint32_t m_acc = 0u;
+        const uint8_t* zb = sZ;
+        uint32_t m_acc[2] = {0u, 0u};
         uint64_t* wait_bar = bar_in;
         uint32_t wait_parity = n & 1;
         if (role == 0) {
@@ -298,42 +320,52 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             const int st = n % kTmStages;
             wait_bar = &bar_z[q][st];
             wait_parity = (n / kTmStages) & 1;
-            za = sZ + st * S::kStage + q * (4 * kTmSlot) + h * (2 * kTmSlot) + t * 128;
+            zb = sZ + st * S::kStage + q * (4 * kTmSlot);
         } else {
-            const TmSeq s = tm_seq_at(P, n, sigma);
-            const int f_in = s.f0 - 3 - L + s.j;           // layer 2 reads H1[f0-4+j], layer 3 reads H2[f0-5+j]
-            // rows outside the grid are the zero padding of the next layer; idle lanes hold zeros
-            m_acc = (t < kT && s.valid && f_in >= 0 && f_in < P.F) ? 0xffffffffu : 0u;
-        }
-        mbar_wait(wait_bar, wait_parity);
-        tc_fence_after_sync();
-        uint32_t v[2][8];
-        tmem_ld8(dsrc, v[0]);
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-            const uint4 z = ld_shared_v4((ch < 8 ? za : za + kTmSlot) + (((ch & 7) ^ swz) << 4));
-            tmem_ld_wait8(v[ch & 1]);
-            if (ch < 15) {
-                tmem_ld8(dsrc + 8 * (ch + 1), v[(ch + 1) & 1]);
-            } else {                                       // accumulator drained
+            for (int h = 0; h < 2; ++h) {
+                const TmSeq s = tm_seq_at(P, n, 2 * q + h);
+                const int f_in = s.f0 - 3 - L + s.j;       // layer 2 reads H1[f0-4+j], layer 3 reads H2[f0-5+j]
+                // rows outside the grid are the zero padding of the next layer; the idle pair holds zeros
+                m_acc[h] = (pi < 7 && s.valid && f_in >= 0 && f_in < P.F) ? 0xffffffffu : 0u;
+            }
+        }
+        mbar_wait_sleep(wait_bar, wait_parity);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t d0[8], d1[8];
+            tmem_ld_16x256b_x2(dsrc + 16 * c, d0);
+            tmem_ld_16x256b_x2(dsrc + (16u << 16) + 16 * c, d1);
+            const float2 bA = *reinterpret_cast<const float2*>(biasL + 16 * c);
+            const float2 bB = *reinterpret_cast<const float2*>(biasL + 16 * c + 8);
+            // input row from shared memory (role 0): channels 16 c + 4 g + {0..3} of `a` (c < 4) or `s | pe`
+            const uint8_t* zc = zb + (c < 4 ? 0 : kTmSlot);
+            const uint2 z00 = lds64_if(zc + box_off(0, c & 3), m_lds), z01 = lds64_if(zc + box_off(1, c & 3), m_lds);
+            const uint2 z10 = lds64_if(zc + 2 * kTmSlot + box_off(0, c & 3), m_lds), z11 = lds64_if(zc + 2 * kTmSlot + box_off(1, c & 3), m_lds);
+            tmem_ld_wait16(d0, d1);
+            if (c == 7) {                                  // accumulator drained
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == drain_lane) mbar_arrive(bar_in_empty);
             }
-            const float4 b0 = *reinterpret_cast<const float4*>(biasL + 8 * ch);
-            const float4 b1 = *reinterpret_cast<const float4*>(biasL + 8 * ch + 4);
-            uint32_t xw[4];                                // bias + ReLU + fp16 | input row from shared memory
-            xw[0] = (pack_relu_half2(__uint_as_float(v[ch & 1][0]) + b0.x, __uint_as_float(v[ch & 1][1]) + b0.y) & m_acc) | (z.x & m_lds);
-            xw[1] = (pack_relu_half2(__uint_as_float(v[ch & 1][2]) + b0.z, __uint_as_float(v[ch & 1][3]) + b0.w) & m_acc) | (z.y & m_lds);
-            xw[2] = (pack_relu_half2(__uint_as_float(v[ch & 1][4]) + b1.x, __uint_as_float(v[ch & 1][5]) + b1.y) & m_acc) | (z.z & m_lds);
-            xw[3] = (pack_relu_half2(__uint_as_float(v[ch & 1][6]) + b1.z, __uint_as_float(v[ch & 1][7]) + b1.w) & m_acc) | (z.w & m_lds);
-            uint32_t o[4];
-            tm_chunk(xw, pa + 4 * ch, pb + 4 * ch, tapL + ch * 36, lane_l, lane_r, o);
-            if (ch == 0 && n >= 1) {                       // the previous GEMM has consumed this layer's A tile
+            uint32_t x[8];                                 // [(h * 2 + px) * 2 + e]: bias + ReLU + fp16 | input row
+            x[0] = (pack_relu_half2(__uint_as_float(d0[0]) + bA.x, __uint_as_float(d0[1]) + bA.y) & m_acc[0]) | z00.x;
+            x[1] = (pack_relu_half2(__uint_as_float(d0[4]) + bB.x, __uint_as_float(d0[5]) + bB.y) & m_acc[0]) | z00.y;
+            x[2] = (pack_relu_half2(__uint_as_float(d0[2]) + bA.x, __uint_as_float(d0[3]) + bA.y) & m_acc[0]) | z01.x;
+            x[3] = (pack_relu_half2(__uint_as_float(d0[6]) + bB.x, __uint_as_float(d0[7]) + bB.y) & m_acc[0]) | z01.y;
+            x[4] = (pack_relu_half2(__uint_as_float(d1[0]) + bA.x, __uint_as_float(d1[1]) + bA.y) & m_acc[1]) | z10.x;
+            x[5] = (pack_relu_half2(__uint_as_float(d1[4]) + bB.x, __uint_as_float(d1[5]) + bB.y) & m_acc[1]) | z10.y;
+            x[6] = (pack_relu_half2(__uint_as_float(d1[2]) + bA.x, __uint_as_float(d1[3]) + bA.y) & m_acc[1]) | z11.x;
+            x[7] = (pack_relu_half2(__uint_as_float(d1[6]) + bB.x, __uint_as_float(d1[7]) + bB.y) & m_acc[1]) | z11.y;
+            uint32_t o[8];
+            tm_chunk(x, pa + 8 * c, pb + 8 * c, tapL + c * 72, lane_l, lane_r, o);
+            if (c == 0 && n >= 1) {                        // the previous GEMM has consumed this layer's A tile
                 mbar_wait(&bar_dfull[L], (n - 1) & 1);
                 tc_fence_after_sync();
             }
-            tmem_st4(adst + 4 * ch, o[0], o[1], o[2], o[3]);
+            tmem_st_16x256b_x1(adst + 8 * c, o[0], o[1], o[2], o[3]);
+            tmem_st_16x256b_x1(adst + (16u << 16) + 8 * c, o[4], o[5], o[6], o[7]);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -344,7 +376,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         }
         __syncwarp();
     }
-    if (role == 0 && t == 0) bulk_wait_all();
+    if (role == 0 && lane < 2) bulk_wait_all();
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);

@@ -347,6 +347,43 @@ __device__ __forceinline__ void umma_gemm_k_ts(uint32_t tmem_d, uint32_t tmem_a,
     }
 }
 
+// 16x256b fragments (tools/tmem_frag_probe.cu): thread T holds TMEM lanes base + T/4 (r0, r1 / r4, r5) and
+// base + T/4 + 8 (r2, r3 / r6, r7), columns col + 2*(T%4) + {0, 1} (r0..r3) and col + 8 + 2*(T%4) + {0, 1} (r4..r7);
+// `taddr` carries the first of the 16 lanes (a multiple of 16 inside the warp's quadrant).
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&a)[8], uint32_t (&b)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+                 :
+                 : "memory");
+}
+// lanes base + T/4: columns col + 2*(T%4) + {0,1} <- a, b;  lanes base + T/4 + 8: same columns <- c, d
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
+// wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of probing in a tight loop that steals issue slots from the warps that work
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (!ok && ++spins > (1u << 22)) __trap();
+    }
+}
+
 // 3-D tensor-map TMA (box lands in the map's swizzle pattern; out-of-range coordinates read zeros
 // and are clipped on stores)
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
