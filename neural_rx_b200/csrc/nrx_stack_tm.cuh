@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         return (px ? row1 : row0) + ((((2 * c) + (g >> 1)) ^ (px ? sw1 : sw0)) << 4) + ((g & 1) << 3);
     };
 
-    // ---- role 0 only: input / residual fetch and the output epilogue (lanes 0 and 1 drive the TMA
-    //      of the warp's two sequences) -------------------------------------------------------------
+    // ---- input fetch (role 0), residual fetch and output epilogue (role 2); lanes 0 and 1 drive the
+    //      TMA of the warp's two sequences ---------------------------------------------------------
     auto issue_z = [&](int m) {
         if (lane < 2) {
             const TmSeq s = tm_seq_at(P, m, 2 * q + lane);
@@ -229,9 +229,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     };
     // bias + residual + fp16 + TMA store of output pass m (accumulator D3)
     auto epilogue = [&](int m) {
-        mbar_wait_sleep(&bar_dfull[2], m & 1);
+        mbar_wait(&bar_dfull[2], m & 1);
         tc_fence_after_sync();
-        mbar_wait_sleep(&bar_res[q], m & 1);
+        mbar_wait(&bar_res[q], m & 1);
         if (lane < 2) bulk_wait_read_all();            // the previous store has read the staging rows
         __syncwarp();
 #pragma unroll 1
@@ -255,9 +255,6 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             sts64(os + box_off(0, c), w0);
             sts64(os + box_off(1, c), w1);
         }
-        tc_fence_before_sync();                            // accumulator drained
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_dempty[2]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane < 2) {
@@ -272,7 +269,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     // consumer has drained the previous accumulator -> issue the layer's GEMM
     auto issue_mma = [&](int L, int n) {
         mbar_wait(&bar_afull[L], n & 1);
-        if (n >= 1) mbar_wait(&bar_dempty[L], (n - 1) & 1);
+        if (n >= 1 && L < 2) mbar_wait(&bar_dempty[L], (n - 1) & 1);   // D3 is drained by this role's own epilogue
         tc_fence_after_sync();
         const uint32_t dcol = L == 0 ? 0u : L == 1 ? 128u : 256u;
         const uint32_t acol = 320u + 64u * uint32_t(L);
@@ -306,22 +303,19 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     // Every warp runs the SAME branch-free instruction stream for the pass body (three specialised
     // bodies exceed the instruction cache): both input paths are executed and the role selects by
     // masks / predicates; the role-dependent barriers sit outside the unrolled body.
-    const int n_end = role == 0 ? n_total + 3 : n_total;
-    for (int n = 0; n < n_end; ++n) {
+    for (int n = 0; n < n_total; ++n) {
         const uint8_t* zb = sZ;
         uint32_t m_acc[2] = {0u, 0u};
         uint64_t* wait_bar = bar_in;
         uint32_t wait_parity = n & 1;
         if (role == 0) {
-            if (n >= 3) epilogue(n - 3);
-            if (n >= 2 && n - 2 < n_total) issue_res(n - 2);
-            if (n >= n_total) continue;
             if (n + 2 < n_total) issue_z(n + 2);
             const int st = n % kTmStages;
             wait_bar = &bar_z[q][st];
             wait_parity = (n / kTmStages) & 1;
             zb = sZ + st * S::kStage + q * (4 * kTmSlot);
         } else {
+            if (role == 2 && n >= 1) issue_res(n - 1);     // residual rows of the output pass this step finishes
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const TmSeq s = tm_seq_at(P, n, 2 * q + h);
@@ -367,6 +361,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             tmem_st_16x256b_x1(adst + 8 * c, o[0], o[1], o[2], o[3]);
             tmem_st_16x256b_x1(adst + (16u << 16) + 8 * c, o[4], o[5], o[6], o[7]);
         }
+        // role 2 also owns the output: the epilogue of the previous pass runs here, in the shadow of the
+        // GEMM that produces this role's next input, and before the GEMM that overwrites D3 is issued
+        if (role == 2 && n >= 1) epilogue(n - 1);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -376,7 +373,11 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         }
         __syncwarp();
     }
-    if (role == 0 && lane < 2) bulk_wait_all();
+    if (role == 2 && n_total > 0) {
+        issue_res(n_total - 1);
+        epilogue(n_total - 1);
+        if (lane < 2) bulk_wait_all();
+    }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
