@@ -1024,6 +1024,12 @@ int nrx_debug_phase_cycles(unsigned long long* out32) {
     if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     return NRX_OK;
 }
+int nrx_debug_tm_cycles(unsigned long long* out32) {
+    unsigned long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, g_tm_cycles, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_tm_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    return NRX_OK;
+}
 #endif
 
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {

@@ -136,6 +136,36 @@ __device__ __forceinline__ void tm_chunk(const uint32_t (&x)[8], uint32_t* pa, u
     }
 }
 
+#ifdef NRX_PHASE_TIMING
+// debug build (tools/tm_phase_timing.py): cycle accounting of CTA 0, lane 0 of the first warp of each role:
+// [3r] input waits, [3r+2] depthwise pass (incl. GEMM issue), [9+r] GEMM issue -> complete, [12+r] wait for
+// the other warps / the consumer before the GEMM issue, [15+r] epilogue, [20] kernel total, [21] steps
+__device__ unsigned long long g_tm_cycles[32];
+#define NRX_TM_TICK(i)                                                     \
+    do {                                                                   \
+        if (tm_timer) {                                                    \
+            const long long now_ = clock64();                              \
+            tm_acc[i] += (unsigned long long)(now_ - tm_last);             \
+            tm_last = now_;                                                \
+        }                                                                  \
+    } while (0)
+#ifdef NRX_TM_FINE                                         // finer: inside the pass body (perturbs the schedule)
+#define NRX_TM_TICK2(i)                                                    \
+    do {                                                                   \
+        if (tm_timer) {                                                    \
+            const long long now_ = clock64();                              \
+            tm_fine[i] += (unsigned long long)(now_ - tm_last2);           \
+            tm_last2 = now_;                                               \
+        }                                                                  \
+    } while (0)
+#else
+#define NRX_TM_TICK2(i) do { } while (0)
+#endif
+#else
+#define NRX_TM_TICK(i) do { } while (0)
+#define NRX_TM_TICK2(i) do { } while (0)
+#endif
+
 // predicated 8-byte shared-memory load (role 0 only reads the input rows)
 __device__ __forceinline__ uint2 lds64_if(const void* p, uint32_t pred) {
     uint2 z = make_uint2(0u, 0u);
@@ -206,6 +236,15 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         return (px ? row1 : row0) + ((((2 * c) + (g >> 1)) ^ (px ? sw1 : sw0)) << 4) + ((g & 1) << 3);
     };
 
+#ifdef NRX_PHASE_TIMING
+    const bool tm_timer = blockIdx.x == 0 && q == 0 && lane == 0;
+    unsigned long long tm_acc[4] = {0, 0, 0, 0};          // waits, -, pass, epilogue
+    unsigned long long tm_mma = 0, tm_mma_wait = 0;
+    unsigned long long tm_fine[4] = {0, 0, 0, 0};         // accumulator load + wait, convert, shuffles + depthwise, A store
+    long long tm_last2 = 0;
+    long long tm_last = clock64();
+    const long long tm_start = tm_last;
+#endif
     // ---- input fetch (role 0), residual fetch and output epilogue (role 2); lanes 0 and 1 drive the
     //      TMA of the warp's two sequences ---------------------------------------------------------
     auto issue_z = [&](int m) {
@@ -268,15 +307,28 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
     // the elected lane of a layer's first warp: all four warps have stored their A rows and the
     // consumer has drained the previous accumulator -> issue the layer's GEMM
     auto issue_mma = [&](int L, int n) {
+#ifdef NRX_PHASE_TIMING
+        const long long t_a = clock64();
+#endif
         mbar_wait(&bar_afull[L], n & 1);
         if (n >= 1 && L < 2) mbar_wait(&bar_dempty[L], (n - 1) & 1);   // D3 is drained by this role's own epilogue
         tc_fence_after_sync();
+#ifdef NRX_PHASE_TIMING
+        const long long t_b = clock64();
+        if (blockIdx.x == 0) tm_mma_wait += (unsigned long long)(t_b - t_a);
+#endif
         const uint32_t dcol = L == 0 ? 0u : L == 1 ? 128u : 256u;
         const uint32_t acol = 320u + 64u * uint32_t(L);
         const uint32_t woff = L == 0 ? 0u : L == 1 ? 32768u : 65536u;
         const uint32_t nn = L == 2 ? 64u : 128u;
         umma_gemm_k_ts(tbase + dcol, tbase + acol, smem_u32(sW + woff), nn * 128u, 128, umma_idesc_f16(128, nn));
         umma_commit(&bar_dfull[L]);
+#ifdef NRX_PHASE_TIMING
+        if (blockIdx.x == 0) {                             // perturbs the schedule: the issuing warp waits for its GEMM
+            mbar_wait(&bar_dfull[L], n & 1);
+            tm_mma += (unsigned long long)(clock64() - t_b);
+        }
+#endif
     };
 
     uint32_t pa[64], pb[64];                               // [chunk 8][h 2][px 2][e 2]
@@ -324,8 +376,13 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
                 m_acc[h] = (pi < 7 && s.valid && f_in >= 0 && f_in < P.F) ? 0xffffffffu : 0u;
             }
         }
+        NRX_TM_TICK(2);                                    // bookkeeping between passes counts as pass time
         mbar_wait_sleep(wait_bar, wait_parity);
         tc_fence_after_sync();
+        NRX_TM_TICK(0);
+#ifdef NRX_TM_FINE
+        tm_last2 = clock64();
+#endif
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             uint32_t d0[8], d1[8];
@@ -338,6 +395,7 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             const uint2 z00 = lds64_if(zc + box_off(0, c & 3), m_lds), z01 = lds64_if(zc + box_off(1, c & 3), m_lds);
             const uint2 z10 = lds64_if(zc + 2 * kTmSlot + box_off(0, c & 3), m_lds), z11 = lds64_if(zc + 2 * kTmSlot + box_off(1, c & 3), m_lds);
             tmem_ld_wait16(d0, d1);
+            NRX_TM_TICK2(0);
             if (c == 7) {                                  // accumulator drained
                 tc_fence_before_sync();
                 __syncwarp();
@@ -353,7 +411,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             x[6] = (pack_relu_half2(__uint_as_float(d1[2]) + bA.x, __uint_as_float(d1[3]) + bA.y) & m_acc[1]) | z11.x;
             x[7] = (pack_relu_half2(__uint_as_float(d1[6]) + bB.x, __uint_as_float(d1[7]) + bB.y) & m_acc[1]) | z11.y;
             uint32_t o[8];
+            NRX_TM_TICK2(1);
             tm_chunk(x, pa + 8 * c, pb + 8 * c, tapL + c * 72, lane_l, lane_r, o);
+            NRX_TM_TICK2(2);
             if (c == 0 && n >= 1) {                        // the previous GEMM has consumed this layer's A tile
                 mbar_wait(&bar_dfull[L], (n - 1) & 1);
                 tc_fence_after_sync();
@@ -363,7 +423,9 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         }
         // role 2 also owns the output: the epilogue of the previous pass runs here, in the shadow of the
         // GEMM that produces this role's next input, and before the GEMM that overwrites D3 is issued
+        NRX_TM_TICK(2);
         if (role == 2 && n >= 1) epilogue(n - 1);
+        NRX_TM_TICK(3);
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -378,6 +440,17 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         epilogue(n_total - 1);
         if (lane < 2) bulk_wait_all();
     }
+#ifdef NRX_PHASE_TIMING
+    if (tm_timer) {
+        for (int i = 0; i < 3; ++i) atomicAdd(&g_tm_cycles[3 * role + i], tm_acc[i]);
+        atomicAdd(&g_tm_cycles[9 + role], tm_mma);
+        atomicAdd(&g_tm_cycles[12 + role], tm_mma_wait);
+        atomicAdd(&g_tm_cycles[15 + role], tm_acc[3]);
+        if (role == 0) atomicAdd(&g_tm_cycles[20], (unsigned long long)(clock64() - tm_start));
+        if (role == 0) atomicAdd(&g_tm_cycles[21], (unsigned long long)n_total);
+        if (role == 1) for (int i = 0; i < 4; ++i) atomicAdd(&g_tm_cycles[22 + i], tm_fine[i]);
+    }
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
