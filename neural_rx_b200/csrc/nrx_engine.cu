@@ -298,24 +298,6 @@ void launch_sep(nrx_engine* e, cudaStream_t st, SepParams p) {
     nrx_sepconv_kernel<KPAD, NPAD, MODE><<<grid, kThreads, SepSmem<KPAD, NPAD>::kTotal, st>>>(p);
 }
 
-void launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const uint8_t* blob, const float* active,
-                int U, int per_slot, int bp) {
-    AggParams ap{};
-    ap.sbuf = s; ap.abuf = a; ap.wblob = blob; ap.active_tx = active;
-    ap.U = U; ap.rows_per_bu = per_slot;
-    ap.tiles_per_b = (per_slot + 127) / 128;
-    ap.num_tiles = ap.tiles_per_b * bp;
-    const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
-    const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
-    Timed t(e, st, NRX_K_AGG);
-    switch (U) {
-        case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
-        case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
-        case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
-        default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
-    }
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 using TensorMapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -332,15 +314,39 @@ TensorMapEncodeFn tensor_map_encoder() {
     return fn;
 }
 
-// [planes][F*14 rows][64] fp16 activation tensor, box = one subcarrier (14 rows x 128 B), 128-byte swizzle
-int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) {
-    const cuuint64_t dims[3] = {64, cuuint64_t(F) * kT, cuuint64_t(planes)};
-    const cuuint64_t strides[2] = {128, cuuint64_t(F) * kT * 128};
-    const cuuint32_t box[3] = {64, kT, 1}, estr[3] = {1, 1, 1};
+// [planes][rows][64] fp16 activation tensor, box = box_rows rows x 128 B, 128-byte swizzle
+int make_rows_map(CUtensorMap* m, const __half* base, int planes, int rows, int box_rows) {
+    if (!tensor_map_encoder()) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled: driver entry point not found");
+    const cuuint64_t dims[3] = {64, cuuint64_t(rows), cuuint64_t(planes)};
+    const cuuint64_t strides[2] = {128, cuuint64_t(rows) * 128};
+    const cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1}, estr[3] = {1, 1, 1};
     const CUresult r = tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+}
+// box = one subcarrier (14 rows) of a (slot, user) plane
+int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) { return make_rows_map(m, base, planes, F * kT, kT); }
+
+int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const uint8_t* blob, const float* active,
+               int U, int per_slot, int bp) {
+    AggParams ap{};
+    const int rc = make_rows_map(&ap.map_s, s, bp * U, per_slot, 128);
+    if (rc) return rc;
+    ap.sbuf = s; ap.abuf = a; ap.wblob = blob; ap.active_tx = active;
+    ap.U = U; ap.rows_per_bu = per_slot;
+    ap.tiles_per_b = (per_slot + 127) / 128;
+    ap.num_tiles = ap.tiles_per_b * bp;
+    const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
+    const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
+    Timed t(e, st, NRX_K_AGG);
+    switch (U) {
+        case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
+        case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
+        case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
+        default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+    }
+    return NRX_OK;
 }
 
 // plan 4: one TMEM-resident UpdateState stack launch
@@ -849,7 +855,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             kp.pair_agg = pair ? 1 : 0;
             for (int it = 0; it < e->num_it; ++it) {
                 if (!pair)
-                    launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
+                    if (const int rc = launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp)) return rc;
                 kp.a_in = pair ? sp_cur : abuf; kp.s_in = s_cur; kp.s_out = s_alt;
                 kp.sp_out = pair && it + 1 < e->num_it ? sp_alt : nullptr;
                 kp.wblob = e->stack_upd_blobs[it];
@@ -890,7 +896,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             sp.stack_index = nullptr;
             sp.default_stack = 0;
             for (int it = 0; it < e->num_it; ++it) {
-                launch_agg(e, st, sbuf, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp);
+                if (const int rc = launch_agg(e, st, sbuf, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp)) return rc;
                 const auto& L = e->upd_layers[it];
                 sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
                 sp.wblob = L[0].blob; sp.blob_bytes = L[0].blob_bytes;

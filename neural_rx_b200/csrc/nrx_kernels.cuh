@@ -15,6 +15,7 @@
 // +-1 subcarrier halo (11 x 14 rows staged in shared memory by one 1-D bulk copy); the symbol
 // axis is entirely inside the tile.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -517,7 +518,9 @@ __global__ void __launch_bounds__(kThreads, 2) nrx_sepconv_kernel(SepParams p) {
 //    user's state, masked sum over the *other* users, 1/(n_active-1) scaling.  One CTA holds the
 //    same 128 resource elements of all U users, so the cross-user reduction is CTA-local.
 // =============================================================================================
-struct AggParams {
+struct alignas(64) AggParams {
+    CUtensorMap map_s;         // state tensor [Bp*U][F*T][64] fp16, box = 128 rows x 64 channels, 128-byte swizzle:
+                               //   a box lands in shared memory as the K-major UMMA A tile (rows past F*T read zeros)
     const __half* sbuf;        // [Bp*U*F*T][64]
     __half* abuf;              // [Bp*U*F*T][64]
     const uint8_t* wblob;      // [W1 image 64x64 | W2 image 64x64 | b1[64] | b2[64]]
@@ -531,26 +534,37 @@ constexpr int kAggMaxU = 4;
 __host__ __device__ constexpr int agg_smem_bytes(int U) { return U * 32768 + ((kAggBlob + 127) / 128) * 128 + 1024; }
 
 template <int U>
-__global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(AggParams p) {
+__global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(const __grid_constant__ AggParams p) {
     constexpr uint32_t TM_COLS = (U <= 1) ? 64 : (U == 2) ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    uint8_t* sA = smem;                      // [U][128 rows][128 B]  state tiles, later the output staging
-    uint8_t* sH = smem + U * 16384;          // [U][128][128 B]       hidden activations
-    uint8_t* sW = smem + U * 32768;
+    // two stages of [U][128 rows][128 B]: the state tiles of a tile arrive by TMA while the previous tile is
+    // processed; a stage then holds, in turn, the state tiles (A of the first GEMM), the hidden activations (A of
+    // the second GEMM, written after the first has consumed the state) and the output staging
+    uint8_t* sW = smem + 2 * U * 16384;
     const float* sB1 = reinterpret_cast<const float*>(sW + 16384);
     const float* sB2 = sB1 + 64;
-    __shared__ uint64_t bar_w, bar_mma;
+    __shared__ uint64_t bar_w, bar_mma, bar_ld[2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
+    auto load_tile = [&](int tile, int stage) {           // thread 0
+        const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
+        mbar_arrive_expect_tx(&bar_ld[stage], U * 16384);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            tma_load_3d(smem + stage * (U * 16384) + u * 16384, &p.map_s, 0, rt * 128, b * U + u, &bar_ld[stage]);
+    };
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_ld[0], 1);
+        mbar_init(&bar_ld[1], 1);
         fence_mbar_init();
         mbar_arrive_expect_tx(&bar_w, kAggBlob);
         bulk_g2s(sW, p.wblob, kAggBlob, &bar_w);
+        if (int(blockIdx.x) < p.num_tiles) load_tile(blockIdx.x, 0);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -561,37 +575,22 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(Agg
     const int q = warp & 3, hcol = warp >> 2;
     const int r = q * 32 + lane;
 
-    // The state rows of the NEXT tile are fetched into registers while the current tile is processed
-    // (software pipelining: the global-load latency used to be exposed in front of every tile).
-    constexpr int NV = U * 128 * 8 / kThreads;        // 16-byte vectors per thread per tile
-    uint4 pre[NV];
-    auto fetch = [&](int tile) {
-        const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
-        const int r0 = rt * 128, valid_rows = min(128, p.rows_per_bu - r0);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int i = tid + v * kThreads;
-            const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
-            pre[v] = make_uint4(0, 0, 0, 0);
-            if (rr < valid_rows)
-                pre[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
-        }
-    };
-    if (int(blockIdx.x) < p.num_tiles) fetch(blockIdx.x);
-
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
-        // ---- stage the (prefetched) state rows of all users into swizzled A tiles -----------
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int i = tid + v * kThreads;
-            const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
-            st_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
+        const int stage = it & 1;
+        uint8_t* sA = smem + stage * (U * 16384);
+        uint8_t* sH = sA;
+        if (tid == 0) {
+            // the other stage was last written by generic stores (hidden tile, staging) of the previous tile
+            if (tile + int(gridDim.x) < p.num_tiles) {
+                fence_proxy_async_smem();
+                load_tile(tile + gridDim.x, stage ^ 1);
+            }
         }
-        if (tile + int(gridDim.x) < p.num_tiles) fetch(tile + gridDim.x);
-        fence_proxy_async_smem();
+        mbar_wait(&bar_ld[stage], (it >> 1) & 1);
         tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
@@ -681,6 +680,7 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(Agg
                 *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
                     ld_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4));
         }
+        fence_proxy_async_smem();                // this stage is refilled by TMA (async proxy) two tiles later
         __syncthreads();
     }
     tc_fence_before_sync();
