@@ -1068,10 +1068,27 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
         }
     }
     const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
-    int C = e->host_chunk > 0 ? e->host_chunk : (batch + 2) / 3;   // default: three chunks in flight, at most 16 slots each
-    if (e->host_chunk <= 0 && C > 16) C = 16;
-    if (C > batch) C = batch;
-    const int n_chunks = (batch + C - 1) / C;
+    // Chunk schedule.  Only the first chunk's H2D copy and the last chunk's D2H copy are not hidden behind
+    // kernels, so the default schedule is tapered: a small first and last chunk (an eighth of the batch each) around
+    // equal middle chunks of at most 16 slots.  nrx_set_host_chunk(n > 0) selects uniform chunks of n slots.
+    std::vector<int> cn;                                // slots per chunk
+    if (e->host_chunk > 0 || batch < 12) {
+        int c = e->host_chunk > 0 ? e->host_chunk : (batch + 2) / 3;
+        if (c > batch) c = batch;
+        for (int b0 = 0; b0 < batch; b0 += c) cn.push_back(batch - b0 < c ? batch - b0 : c);
+    } else {
+        const int edge = (batch + 7) / 8, rem = batch - 2 * edge, k = (rem + 15) / 16 < 2 ? 2 : (rem + 15) / 16;
+        cn.push_back(edge);
+        for (int j = 0; j < k; ++j) cn.push_back(rem / k + (j < rem % k ? 1 : 0));
+        cn.push_back(edge);
+    }
+    const int n_chunks = int(cn.size());
+    std::vector<int> cb0(n_chunks, 0);                  // first slot of every chunk
+    int C = 0;                                          // largest chunk: sizes the ring buffers
+    for (int i = 0; i < n_chunks; ++i) {
+        cb0[i] = i ? cb0[i - 1] + cn[i - 1] : 0;
+        if (cn[i] > C) C = cn[i];
+    }
     // bytes per slot of every stream of data
     const size_t y_slot = size_t(d.num_rx_ant) * per_slot * 8;
     float* outs[4] = {llr, llr_grid, h_hat_refined, h_hat_ls};
@@ -1131,7 +1148,7 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
     NRX_CUDA(cudaMemcpyAsync(dp, hp, small_bytes, cudaMemcpyHostToDevice, e->s_h2d));
 
     auto drain = [&](int i) -> int {                   // chunk i: wait for its D2H, un-stage pageable outputs
-        const int r = i % R, b0 = i * C, n = batch - b0 < C ? batch - b0 : C;
+        const int r = i % R, b0 = cb0[i], n = cn[i];
         NRX_CUDA(cudaEventSynchronize(e->ev_d2h[r]));
         for (int k = 0; k < 4; ++k)
             if (outs[k] && !out_pinned[k])
@@ -1139,7 +1156,7 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
         return NRX_OK;
     };
     for (int i = 0; i < n_chunks; ++i) {
-        const int r = i % R, b0 = i * C, n = batch - b0 < C ? batch - b0 : C;
+        const int r = i % R, b0 = cb0[i], n = cn[i];
         if (i >= R) { const int rc = drain(i - R); if (rc) return rc; }
         const uint8_t* ysrc = static_cast<const uint8_t*>(y) + size_t(b0) * y_slot;
         if (!y_pinned) {
