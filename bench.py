@@ -328,7 +328,7 @@ def main():
     h2d = ys_pin[0].nbytes + base.active_tx.nbytes
     d2h = sum(v.nbytes for v in res.values())
     e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "host_memory": "pinned", "host_chunk_slots": args.host_chunk or "tapered (B/8 first and last, <= 16 between)"}
+           "d2h_bytes_per_step": int(d2h), "host_memory": "pinned", "host_chunk_slots": args.host_chunk or min(16, (B + 2) // 3)}
     # same call with ordinary (pageable) NumPy arrays, staged through the engine's pinned buffers
     t0 = time.perf_counter()
     for i in range(max(args.steps // 2, 1)):

@@ -1068,19 +1068,15 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
         }
     }
     const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
-    // Chunk schedule.  Only the first chunk's H2D copy and the last chunk's D2H copy are not hidden behind
-    // kernels, so the default schedule is tapered: a small first and last chunk (an eighth of the batch each) around
-    // equal middle chunks of at most 16 slots.  nrx_set_host_chunk(n > 0) selects uniform chunks of n slots.
+    // Chunk schedule: uniform chunks, by default a third of the batch and at most 16 slots (three chunks in flight).
+    // A tapered schedule (small first and last chunk, so that less of the first H2D / last D2H copy is exposed) was
+    // measured equal with pinned buffers and slower with pageable ones: the un-hidden cost is per chunk, not per byte.
     std::vector<int> cn;                                // slots per chunk
-    if (e->host_chunk > 0 || batch < 12) {
+    {
         int c = e->host_chunk > 0 ? e->host_chunk : (batch + 2) / 3;
+        if (e->host_chunk <= 0 && c > 16) c = 16;
         if (c > batch) c = batch;
         for (int b0 = 0; b0 < batch; b0 += c) cn.push_back(batch - b0 < c ? batch - b0 : c);
-    } else {
-        const int edge = (batch + 7) / 8, rem = batch - 2 * edge, k = (rem + 15) / 16 < 2 ? 2 : (rem + 15) / 16;
-        cn.push_back(edge);
-        for (int j = 0; j < k; ++j) cn.push_back(rem / k + (j < rem % k ? 1 : 0));
-        cn.push_back(edge);
     }
     const int n_chunks = int(cn.size());
     std::vector<int> cb0(n_chunks, 0);                  // first slot of every chunk
