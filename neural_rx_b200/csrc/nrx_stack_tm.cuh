@@ -93,44 +93,58 @@ __host__ __device__ constexpr int tm_phys_col(int n) { return (n & ~15) | ((n & 
 // chunk, [tap 0..8][g][e] (tp already points at g).  A thread's symbols are adjacent (2i, 2i+1): only
 // the outer neighbours come from other lanes (pair i-1 / i+1 = lane T-4 / T+4).  Tap order and
 // accumulation order per output are those of dw_slide (nrx_stack.cuh).
-__device__ __forceinline__ void tm_chunk(const uint32_t (&x)[8], uint32_t* pa, uint32_t* pb, const uint32_t* tp, int lane_l,
-                                         int lane_r, uint32_t (&o)[8]) {
-    // index = (h * 2 + px) * 2 + e
-    __half2 in[3][8], e[8], a[8], b[8];
+struct TmIn {            // the three inputs of every output of a chunk: symbols t-1, t, t+1; index = (h * 2 + px) * 2 + e
+    __half2 v[3][8];
+};
+// phase 1: neighbour exchange + the three taps that complete output row r (returned in o)
+__device__ __forceinline__ void tm_chunk_complete(const uint32_t (&x)[8], const uint32_t* pa, const uint32_t* tp, int lane_l,
+                                                  int lane_r, TmIn& in, uint32_t (&o)[8]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int ee = 0; ee < 2; ++ee) {
             const int i0 = (h * 2 + 0) * 2 + ee, i1 = (h * 2 + 1) * 2 + ee;
             const __half2 x0 = u2h(x[i0]), x1 = u2h(x[i1]);
-            in[0][i0] = u2h(__shfl_sync(0xffffffffu, x[i1], lane_l));    // symbol 2i-1
-            in[1][i0] = x0;
-            in[2][i0] = x1;
-            in[0][i1] = x0;
-            in[1][i1] = x1;
-            in[2][i1] = u2h(__shfl_sync(0xffffffffu, x[i0], lane_r));    // symbol 2i+2
+            in.v[0][i0] = u2h(__shfl_sync(0xffffffffu, x[i1], lane_l));    // symbol 2i-1
+            in.v[1][i0] = x0;
+            in.v[2][i0] = x1;
+            in.v[0][i1] = x0;
+            in.v[1][i1] = x1;
+            in.v[2][i1] = u2h(__shfl_sync(0xffffffffu, x[i0], lane_r));    // symbol 2i+2
         }
+    __half2 e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = u2h(pa[i]);
+#pragma unroll
+    for (int tap = 6; tap < 9; ++tap) {
+        const uint2 tv = *reinterpret_cast<const uint2*>(tp + 8 * tap);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = __hfma2(in.v[tap % 3][i], u2h((i & 1) ? tv.y : tv.x), e[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = h2u(e[i]);
+}
+// phase 2: the pending sums of rows r+1 (taps 3, 4, 5 on top of pb) and r+2 (taps 0, 1, 2 from zero)
+__device__ __forceinline__ void tm_chunk_pending(const TmIn& in, uint32_t* pa, uint32_t* pb, const uint32_t* tp) {
+    __half2 a[8], b[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        e[i] = u2h(pa[i]);
         a[i] = u2h(pb[i]);
         b[i] = __float2half2_rn(0.f);
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int tap = k < 3 ? 6 + k : k < 6 ? k : k - 6;       // 6,7,8 (row r) | 3,4,5 (row r+1) | 0,1,2 (row r+2)
+    for (int k = 0; k < 6; ++k) {
+        const int tap = k < 3 ? 3 + k : k - 3;
         const uint2 tv = *reinterpret_cast<const uint2*>(tp + 8 * tap);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const __half2 w = u2h((i & 1) ? tv.y : tv.x);
-            if (k < 3) e[i] = __hfma2(in[tap % 3][i], w, e[i]);
-            else if (k < 6) a[i] = __hfma2(in[tap % 3][i], w, a[i]);
-            else b[i] = __hfma2(in[tap % 3][i], w, b[i]);
+            if (k < 3) a[i] = __hfma2(in.v[tap % 3][i], w, a[i]);
+            else b[i] = __hfma2(in.v[tap % 3][i], w, b[i]);
         }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        o[i] = h2u(e[i]);
         pa[i] = h2u(a[i]);
         pb[i] = h2u(b[i]);
     }
@@ -274,25 +288,36 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
         if (lane < 2) bulk_wait_read_all();            // the previous store has read the staging rows
         __syncwarp();
 #pragma unroll 1
-        for (int hc = 0; hc < 8; ++hc) {
-            const int h = hc >> 2, c = hc & 3;
-            uint32_t r[8], dummy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            tmem_ld_16x256b_x2(tlane + (uint32_t(16 * h) << 16) + 256 + 16 * c, r);
+        for (int hc = 0; hc < 4; ++hc) {                   // two 16-column groups per iteration: both TMEM loads in flight
+            const int h = hc >> 1, c0 = (hc & 1) * 2;
+            uint32_t r0[8], r1[8];
+            tmem_ld_16x256b_x2(tlane + (uint32_t(16 * h) << 16) + 256 + 16 * c0, r0);
+            tmem_ld_16x256b_x2(tlane + (uint32_t(16 * h) << 16) + 256 + 16 * (c0 + 1), r1);
             const uint8_t* rs = sRes + q * (2 * kTmSlot) + h * kTmSlot;
             uint8_t* os = sOut + q * (2 * kTmSlot) + h * kTmSlot;
-            const float2 bA = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 2 * g);
-            const float2 bB = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 8 + 2 * g);
-            const uint2 old0 = lds64(rs + box_off(0, c)), old1 = lds64(rs + box_off(1, c));
-            tmem_ld_wait16(r, dummy);
-            const float2 o00 = __half22float2(u2h(old0.x)), o01 = __half22float2(u2h(old0.y));
-            const float2 o10 = __half22float2(u2h(old1.x)), o11 = __half22float2(u2h(old1.y));
-            uint2 w0, w1;                              // s <- s + update (:266)
-            w0.x = pack_half2((__uint_as_float(r[0]) + bA.x) + o00.x, (__uint_as_float(r[1]) + bA.y) + o00.y);
-            w0.y = pack_half2((__uint_as_float(r[4]) + bB.x) + o01.x, (__uint_as_float(r[5]) + bB.y) + o01.y);
-            w1.x = pack_half2((__uint_as_float(r[2]) + bA.x) + o10.x, (__uint_as_float(r[3]) + bA.y) + o10.y);
-            w1.y = pack_half2((__uint_as_float(r[6]) + bB.x) + o11.x, (__uint_as_float(r[7]) + bB.y) + o11.y);
-            sts64(os + box_off(0, c), w0);
-            sts64(os + box_off(1, c), w1);
+            uint2 old[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                old[j][0] = lds64(rs + box_off(0, c0 + j));
+                old[j][1] = lds64(rs + box_off(1, c0 + j));
+            }
+            tmem_ld_wait16(r0, r1);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t(&r)[8] = j ? r1 : r0;
+                const int c = c0 + j;
+                const float2 bA = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 2 * g);
+                const float2 bB = *reinterpret_cast<const float2*>(sBias + 256 + 16 * c + 8 + 2 * g);
+                const float2 o00 = __half22float2(u2h(old[j][0].x)), o01 = __half22float2(u2h(old[j][0].y));
+                const float2 o10 = __half22float2(u2h(old[j][1].x)), o11 = __half22float2(u2h(old[j][1].y));
+                uint2 w0, w1;                              // s <- s + update (:266)
+                w0.x = pack_half2((__uint_as_float(r[0]) + bA.x) + o00.x, (__uint_as_float(r[1]) + bA.y) + o00.y);
+                w0.y = pack_half2((__uint_as_float(r[4]) + bB.x) + o01.x, (__uint_as_float(r[5]) + bB.y) + o01.y);
+                w1.x = pack_half2((__uint_as_float(r[2]) + bA.x) + o10.x, (__uint_as_float(r[3]) + bA.y) + o10.y);
+                w1.y = pack_half2((__uint_as_float(r[6]) + bB.x) + o11.x, (__uint_as_float(r[7]) + bB.y) + o11.y);
+                sts64(os + box_off(0, c), w0);
+                sts64(os + box_off(1, c), w1);
+            }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -383,11 +408,15 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
 #ifdef NRX_TM_FINE
         tm_last2 = clock64();
 #endif
+        if (n >= 1) {                                      // the previous GEMM has consumed this layer's A tile
+            mbar_wait(&bar_dfull[L], (n - 1) & 1);
+            tc_fence_after_sync();
+        }
+        uint32_t d0[8], d1[8];                             // accumulator fragments of the two sequences
+        tmem_ld_16x256b_x2(dsrc, d0);
+        tmem_ld_16x256b_x2(dsrc + (16u << 16), d1);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            uint32_t d0[8], d1[8];
-            tmem_ld_16x256b_x2(dsrc + 16 * c, d0);
-            tmem_ld_16x256b_x2(dsrc + (16u << 16) + 16 * c, d1);
             const float2 bA = *reinterpret_cast<const float2*>(biasL + 16 * c);
             const float2 bB = *reinterpret_cast<const float2*>(biasL + 16 * c + 8);
             // input row from shared memory (role 0): channels 16 c + 4 g + {0..3} of `a` (c < 4) or `s | pe`
@@ -410,19 +439,19 @@ __global__ void __launch_bounds__(kTmThreads, 1) nrx_stack_tm_kernel(const __gri
             x[5] = (pack_relu_half2(__uint_as_float(d1[4]) + bB.x, __uint_as_float(d1[5]) + bB.y) & m_acc[1]) | z10.y;
             x[6] = (pack_relu_half2(__uint_as_float(d1[2]) + bA.x, __uint_as_float(d1[3]) + bA.y) & m_acc[1]) | z11.x;
             x[7] = (pack_relu_half2(__uint_as_float(d1[6]) + bB.x, __uint_as_float(d1[7]) + bB.y) & m_acc[1]) | z11.y;
-            uint32_t o[8];
             NRX_TM_TICK2(1);
-            tm_chunk(x, pa + 8 * c, pb + 8 * c, tapL + c * 72, lane_l, lane_r, o);
-            NRX_TM_TICK2(2);
-            if (c == 0 && n >= 1) {                        // the previous GEMM has consumed this layer's A tile
-                mbar_wait(&bar_dfull[L], (n - 1) & 1);
-                tc_fence_after_sync();
-            }
+            TmIn in;
+            uint32_t o[8];
+            tm_chunk_complete(x, pa + 8 * c, tapL + c * 72, lane_l, lane_r, in, o);
             tmem_st_16x256b_x1(adst + 8 * c, o[0], o[1], o[2], o[3]);
             tmem_st_16x256b_x1(adst + (16u << 16) + 8 * c, o[4], o[5], o[6], o[7]);
+            if (c < 7) {                                   // next chunk's accumulator fragments arrive during phase 2
+                tmem_ld_16x256b_x2(dsrc + 16 * (c + 1), d0);
+                tmem_ld_16x256b_x2(dsrc + (16u << 16) + 16 * (c + 1), d1);
+            }
+            tm_chunk_pending(in, pa + 8 * c, pb + 8 * c, tapL + c * 72);
+            NRX_TM_TICK2(2);
         }
-        // role 2 also owns the output: the epilogue of the previous pass runs here, in the shadow of the
-        // GEMM that produces this role's next input, and before the GEMM that overwrites D3 is issued
         NRX_TM_TICK(2);
         if (role == 2 && n >= 1) epilogue(n - 1);
         NRX_TM_TICK(3);
