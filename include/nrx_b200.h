@@ -101,6 +101,11 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  *                         Bit-identical; measured 31 % slower than plan 1 because the two
  *                         cluster-scope hand-shakes per GEMM sit on the serial chain.  Kept as the
  *                         base of the next kernel generation (ROADMAP.md);
+ *   fused == 4:           as 1, but the UpdateState stacks run in the TMEM-resident kernel
+ *                         (nrx_stack_tm.cuh: depthwise results written to tensor memory and used
+ *                         as the A operand of tcgen05.mma, register line buffers, tensor-map TMA;
+ *                         needs cuTensorMapEncodeTiled from the driver).  Bit-identical to plan 1;
+ *                         measured 20 % slower per stack launch;
  *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
  * All plans compute the same function; the others are kept as cross-checks. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);

@@ -925,6 +925,8 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
         rp.tiles_per_bu = (per_slot + 127) / 128;
         rp.num_tiles = rp.tiles_per_bu * BU;
         rp.default_head = llr_head;
+        rp.vec = ((reinterpret_cast<uintptr_t>(rp.llr) | reinterpret_cast<uintptr_t>(rp.llr_grid) |
+                   reinterpret_cast<uintptr_t>(rp.h_ref)) & 15u) == 0;
         const int grid = rp.num_tiles < e->num_sms ? rp.num_tiles : e->num_sms;
         {
             Timed t(e, st, NRX_K_READOUT);

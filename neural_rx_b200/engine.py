@@ -190,7 +190,8 @@ class NrxEngine:
     def set_fused(self, fused) -> None:
         """1/True: fused stack kernels + aggregation kernel (default); 2: fused stacks with the
         message MLP in their tail (two users); 3: CTA-pair stack kernels (cta_group::2 GEMMs, half the
-        weights per CTA; experimental); 0/False: one kernel per SeparableConv2D layer."""
+        weights per CTA; experimental); 4: TMEM-resident UpdateState stacks (experimental); 0/False: one kernel
+        per SeparableConv2D layer."""
         self._check(self._lib.nrx_set_fused(self._h, int(fused)))
 
     def set_host_chunk(self, slots: int) -> None:
