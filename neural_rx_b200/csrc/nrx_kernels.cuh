@@ -590,6 +590,11 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
                 load_tile(tile + gridDim.x, stage ^ 1);
             }
         }
+        // activity flags of the slot: fetched now, used in the output epilogue (the load used to sit there with its
+        // full latency)
+        float m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) m[u] = __ldg(p.active_tx + b * U + u);
         mbar_wait(&bar_ld[stage], (it >> 1) & 1);
         tc_fence_before_sync();
         __syncthreads();
@@ -638,12 +643,9 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
         tc_fence_after_sync();
         // ---- output epilogue: masked sum over the other users (:192-204) -> staging in sA ------
         {
-            float m[U], n_act = 0.f;
+            float n_act = 0.f;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                m[u] = p.active_tx[b * U + u];
-                n_act += m[u];
-            }
+            for (int u = 0; u < U; ++u) n_act += m[u];
             const float pm = fmaxf(n_act - 1.f, 0.f);
             const float scale = (pm == 0.f) ? 1.f : 1.f / pm;
             const int col = hcol * 32;
@@ -781,6 +783,13 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
             st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
         }
         if (tile + int(gridDim.x) < p.num_tiles) fetch(tile + gridDim.x);
+        // demapped position of this thread's row: fetched now, used after the second GEMM (the load used to sit,
+        // with its full latency, on the four warps of the output epilogue)
+        int d_row = -1;
+        if (warp < 4 && p.llr && r < valid_rows) {
+            const int prow = r0 + r, f = prow / kT, t = prow - f * kT;
+            d_row = __ldg(p.data_index + t * p.F + f);
+        }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -849,10 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
                     }
                 };
                 if (p.llr_grid) store_bits(p.llr_grid + grow * p.out_bits);
-                if (p.llr) {
-                    const int d = p.data_index[t * p.F + f];
-                    if (d >= 0) store_bits(p.llr + (size_t(bu) * p.n_data + d) * p.out_bits);
-                }
+                if (p.llr && d_row >= 0) store_bits(p.llr + (size_t(bu) * p.n_data + d_row) * p.out_bits);
                 if (p.llr_aerial) {
                     const int bb = bu / p.U, uu = bu - bb * p.U;
 #pragma unroll
