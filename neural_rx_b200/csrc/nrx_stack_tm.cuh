@@ -5,29 +5,35 @@
 // touch shared memory.
 //
 //   * An MMA row (TMEM lane) is one resource element (f, t).  A warp owns the 32 lanes of its TMEM
-//     quadrant = two *sequences* (lanes 0-13 and 16-29: the 14 OFDM symbols of one subcarrier each;
-//     lanes 14, 15, 30, 31 idle).  A CTA therefore advances 8 sequences in lock step; a sequence
-//     walks down its own range of subcarriers (a *job*) one subcarrier per step.
-//   * Depthwise 3x3 in "scatter" form: the thread that holds input row f of its pixel adds the
+//     quadrant = two *sequences* (16 lanes each: lanes 0-6 the even, 8-14 the odd OFDM symbols of one
+//     subcarrier; lanes 7 and 15 idle).  A CTA therefore advances 8 sequences in lock step; a
+//     sequence walks down its own range of subcarriers (a *job*) one subcarrier per step.
+//   * With the 16x256b fragment of tcgen05.ld / tcgen05.st (tools/tmem_frag_probe.cu) thread T owns,
+//     in both sequences of its warp, the adjacent symbols (2i, 2i+1), i = T/4, and per 16-channel
+//     group the four consecutive channels 4g .. 4g+3, g = T%4.
+//   * Depthwise 3x3 in "scatter" form: the thread that holds input row f of its pixels adds the
 //     row's contribution to the pending outputs f-1 (which completes), f and f+1, so the +-1
 //     subcarrier halo lives in registers (2 x 64 half2 pending sums per thread) and the +-1 symbol
-//     halo comes from the neighbouring lanes by warp shuffles.  The nine taps and the biases are
-//     kernel parameters (constant bank): every lane of a warp works on the same channel.
+//     halo is one shuffle per pixel-column from lane T-4 / T+4.  Taps and biases sit in shared
+//     memory (copied from the kernel parameters) and are read as 8-byte broadcast loads.
 //   * The completed depthwise row is written to tensor memory (tcgen05.st) and is the A operand
 //     of tcgen05.mma (A in TMEM, B = pointwise weights resident in shared memory, D in TMEM).
-//     The next layer's warps read D with tcgen05.ld in exactly the row-per-lane mapping they need:
-//     bias + ReLU + fp16 in registers, straight into their own depthwise pass.
+//     The next layer's warps read D with tcgen05.ld in exactly the fragment they need (output
+//     channels are stored in fragment order, tm_phys_col): bias + ReLU + fp16 in registers, straight
+//     into their own depthwise pass.
 //   * Warp roles: warps 0-3 layer 1 (input rows by tensor-map TMA, 128B swizzle -> conflict-free
-//     row-per-lane reads) + output epilogue (bias, residual, TMA store); warps 4-7 layer 2;
-//     warps 8-11 layer 3.  The three layers work on consecutive steps concurrently; mbarriers
-//     (A full / D full / D empty per layer) are the only cross-warp synchronisation.
+//     fragment reads); warps 4-7 layer 2; warps 8-11 layer 3 + output epilogue (bias, residual, TMA
+//     store).  The three layers work on consecutive steps concurrently; mbarriers (A full / D full /
+//     D empty per layer) are the only cross-warp synchronisation.  All roles execute one
+//     branch-free pass body (predicated loads, masks): three bodies do not fit the instruction cache.
 //
 // Tensor memory (512 columns): D1 [0,128) D2 [128,256) D3 [256,320) A1 [320,384) A2 [384,448)
 // A3 [448,512).  Shared memory: pointwise weights 80 KB | input ring 3 x 32 KB | residual 16 KB |
 // output staging 16 KB.
 //
 // The accumulation order of every fp16 / fp32 sum equals the one of nrx_stack_kernel, so the two
-// plans are expected to agree bit for bit (tests/test_gpu_parity.py::test_tm_plan_equals_fused).
+// plans agree bit for bit (tests/test_gpu_parity.py::test_fused_equals_layerwise, test_tm_plan_job_split).
+// Measured slower than plan 1 (0.545 vs 0.45 ms per launch): DESIGN.md 4.8, ROADMAP.md 6.
 #pragma once
 #include <cuda.h>
 
