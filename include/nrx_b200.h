@@ -167,6 +167,18 @@ int nrx_set_host_chunk(nrx_engine* e, int32_t slots);
 /* Number of kernels nrx_forward enqueues for `batch` slots with the current settings. */
 int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launches);
 
+/* Host-only planning helpers (pure functions, no device needed; exported for tests and tooling).
+ *   nrx_plan_stack_chunks: plans 1-3 cut every (slot, user) plane of `num_subcarriers` into that many chunks of
+ *                          consecutive subcarriers (one work item each; minimises waves x steps on num_sms CTAs);
+ *   nrx_plan_stack_jobs:   plan 4 cuts a plane into jobs; eight jobs form one item that a CTA advances in lock step
+ *                          for steps_per_item steps (longest job + 6 pipeline-fill steps);
+ *   nrx_fragment_column:   physical accumulator column in which plan 4's weight images keep output channel
+ *                          `channel` (the 16x256b tcgen05 fragment order; a permutation inside every 16 channels). */
+int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* chunks_per_plane);
+int nrx_plan_stack_jobs(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* jobs_per_plane, int32_t* num_items,
+                        int32_t* steps_per_item);
+int nrx_fragment_column(int32_t channel);
+
 /* Algorithmic multiply-accumulates per user resource element for head `llr_head` at the current
  * num_it (sum of weight elements, biases excluded — SURVEY.md App. A.6). */
 int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);

@@ -742,6 +742,24 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
     return NRX_OK;
 }
 
+// Host-only planning helpers (no device needed): how the stack kernels cut the subcarrier axis.
+int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* chunks_per_plane) {
+    if (planes < 1 || num_subcarriers < 1 || num_sms < 1 || !chunks_per_plane) return fail(NRX_ERR_INVALID, "nrx_plan_stack_chunks: bad argument");
+    *chunks_per_plane = choose_chunks(planes, num_subcarriers, num_sms);
+    return NRX_OK;
+}
+int nrx_plan_stack_jobs(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* jobs_per_plane, int32_t* num_items,
+                        int32_t* steps_per_item) {
+    if (planes < 1 || num_subcarriers < 1 || num_sms < 1 || !jobs_per_plane || !num_items || !steps_per_item)
+        return fail(NRX_ERR_INVALID, "nrx_plan_stack_jobs: bad argument");
+    const int j = tm_choose_jobs(planes, num_subcarriers, num_sms);
+    *jobs_per_plane = j;
+    *num_items = (planes * j + kTmSeqs - 1) / kTmSeqs;
+    *steps_per_item = (num_subcarriers + j - 1) / j + kTmFill;
+    return NRX_OK;
+}
+int nrx_fragment_column(int32_t channel) { return channel < 0 ? -1 : tm_phys_col(channel); }
+
 int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs) {
     if (!e || !macs || llr_head < 0 || llr_head >= e->d.n_io) return fail(NRX_ERR_INVALID, "nrx_mac_per_pixel: bad argument");
     *macs = e->mac_fixed[llr_head] + e->mac_per_it * e->num_it;

@@ -24,6 +24,7 @@ NRX_MAX_DMRS = 4
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
+    "nrx_plan_stack_chunks", "nrx_plan_stack_jobs", "nrx_fragment_column",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
 
@@ -89,6 +90,11 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_forward_aerial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, f32p, f32p, f32p, f32p, f32p,
                                        f32p, f32p, ctypes.c_void_p, ctypes.c_size_t]
     lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+    i32o = ctypes.POINTER(ctypes.c_int32)
+    lib.nrx_plan_stack_chunks.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i32o]
+    lib.nrx_plan_stack_jobs.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i32o, i32o, i32o]
+    lib.nrx_fragment_column.argtypes = [ctypes.c_int32]
+    lib.nrx_fragment_column.restype = ctypes.c_int32
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_get_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
