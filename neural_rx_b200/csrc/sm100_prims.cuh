@@ -380,9 +380,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();
-    }
-}
+        if (!ok && ++spins > (1u << 22)) __trap();        // a probe returns after tens of cycles (measured: ~85 probes per
+    }                                                     // 3 k-cycle wait), so the bound is ~0.1 s: a lost arrive surfaces as a
+}                                                         // CUDA error, never as a hang
 
 // 3-D tensor-map TMA (box lands in the map's swizzle pattern; out-of-range coordinates read zeros
 // and are clipped on stores)
