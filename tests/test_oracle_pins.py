@@ -1,7 +1,7 @@
 """CPU tests: the oracle against every artefact of the reference that pins this path
  — weight-list layout and Keras parameter counts, TensorRT binding shapes,
 the PUSCH geometry dump — plus its own committed golden vectors and self-consistency properties.
-LLR-level parity is unpinned by the reference (no golden vectors exist there)."""
+The end-to-end pins (reference forward code executed on seeded slots) live in test_ref_e2e_pins.py."""
 import os
 
 import numpy as np
@@ -293,9 +293,7 @@ def test_aerial_preprocessing_matches_reference_class():
     assert np.abs(pe * np.sqrt((n - 1) / n) - ref_pe).max() <= 1e-5
     assert np.abs(g["aer_pe"][:, :12] - g["aer_pe"][:, 12:]).max() == 0      # tiled over the PRBs
     # FOCC removal: [B, 2N, U, n_p] in the reference, [B, n_p, U, 2N] in the oracle's input convention
-    h = np.transpose(g["focc_in"], (0, 3, 2, 1))
-    B, n_p, U, C = h.shape
-    hf = np.repeat(h.reshape(B, n_p // 2, 2, U, C).sum(axis=2, keepdims=True) / 2.0, 2, axis=2).reshape(B, n_p, U, C)
+    hf = O.aerial_focc_removal(np.transpose(g["focc_in"], (0, 3, 2, 1)))
     assert np.abs(np.transpose(hf, (0, 3, 2, 1)) - g["focc_out"]).max() <= 1e-6
 
 
