@@ -19,6 +19,7 @@
 #include "nrx_stack.cuh"
 #include "nrx_stack_pair.cuh"
 #include "nrx_stack_tm.cuh"
+#include "nrx_stack_ws.cuh"
 
 using namespace nrx;
 
@@ -93,6 +94,8 @@ struct nrx_engine {
     uint8_t* readout_blob = nullptr;                // [n_io] heads
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
+    struct StackBias { float v[320]; };             // host copies of the stack biases [128 | 128 | 64]: kernel parameters of
+    std::vector<StackBias> init_bias, upd_bias;     //   the pipelined stack kernel (per StateInit stack / per iteration)
     uint8_t* pair_init_blob = nullptr;              // CTA-pair kernels: [n_io][2 ranks] half-weight images
     std::vector<uint8_t*> pair_upd_blobs;           // [it] -> [2 ranks]
     struct TmConsts { uint32_t tap[3][64][9]; float bias[320]; };
@@ -325,6 +328,18 @@ int make_rows_map(CUtensorMap* m, const __half* base, int planes, int rows, int 
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
 }
+// [planes][rows][ch] fp16 activation tensor, box = box_rows rows x ch channels, no swizzle: the layer-1 window of
+// the pipelined stack kernel (rows before / after the plane read zeros = the 'same' padding of the first layer)
+int make_window_map(CUtensorMap* m, const __half* base, int planes, int rows, int ch, int box_rows) {
+    if (!tensor_map_encoder()) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled: driver entry point not found");
+    const cuuint64_t dims[3] = {cuuint64_t(ch), cuuint64_t(rows), cuuint64_t(planes)};
+    const cuuint64_t strides[2] = {cuuint64_t(ch) * 2, cuuint64_t(rows) * ch * 2};
+    const cuuint32_t box[3] = {cuuint32_t(ch), cuuint32_t(box_rows), 1}, estr[3] = {1, 1, 1};
+    const CUresult r = tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+}
 // box = one subcarrier (14 rows) of a (slot, user) plane
 int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) { return make_rows_map(m, base, planes, F * kT, kT); }
 
@@ -346,6 +361,29 @@ int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const
         case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
         default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
     }
+    return NRX_OK;
+}
+
+// plan 5: one launch of the warp-specialised, pipelined stack kernel (nrx_stack_ws.cuh)
+template <int MODE>
+int launch_stack_ws(nrx_engine* e, cudaStream_t st, StackParams kp, int planes, int F, const float* bias) {
+    WsParams wp{};
+    memcpy(wp.bias, bias, sizeof wp.bias);
+    int rc;
+    if (MODE == kStackInit) rc = make_window_map(&wp.map_a, kp.z0, planes, F * kT, 32, kWsWin * kT);
+    else {
+        rc = make_window_map(&wp.map_a, kp.a_in, planes, F * kT, 64, kWsWin * kT);
+        if (!rc) rc = make_window_map(&wp.map_s, kp.s_in, planes, F * kT, 64, kWsWin * kT);
+    }
+    if (rc) return rc;
+    kp.n_chunks = ws_choose_chunks(planes, F, e->num_sms);
+    kp.num_items = kp.n_chunks * planes;
+    kp.sp_out = nullptr;
+    kp.pair_agg = 0;
+    wp.p = kp;
+    const int grid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
+    Timed t(e, st, MODE == kStackInit ? NRX_K_STACK_INIT : NRX_K_STACK_UPD);
+    nrx_stack_ws_kernel<MODE><<<grid, kWsThreads, WsSmem<MODE>::kTotal, st>>>(wp);
     return NRX_OK;
 }
 
@@ -476,6 +514,11 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             if (weight_sizes[a0] == int64_t(d.d_s) * d.units_agg && weight_sizes[a0 + 2] == int64_t(d.units_agg) * d.d_s)
                 pack_stack_agg<kStackInit>(host.data() + size_t(m) * LI::kBlob, weight_arrays, a0, d.d_s, d.units_agg);
         }
+        for (int m = 0; m < d.n_io; ++m) {
+            nrx_engine::StackBias sb{};
+            memcpy(sb.v, host.data() + size_t(m) * LI::kBlob + LI::oBias, sizeof sb.v);
+            e->init_bias.push_back(sb);
+        }
         if (cudaMalloc(&e->stack_init_blob, host.size()) != cudaSuccess ||
             cudaMemcpy(e->stack_init_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading StateInit stack weights failed"));
@@ -552,6 +595,11 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                 if (weight_sizes[an] != int64_t(d.d_s) * d.units_agg || weight_sizes[an + 2] != int64_t(d.units_agg) * d.d_s)
                     return bail(fail(NRX_ERR_INVALID, "AggregateUserStates Dense layers expected at weight index %d", an));
                 pack_stack_agg<kStackUpdate>(sb.data(), weight_arrays, an, d.d_s, d.units_agg);
+            }
+            {
+                nrx_engine::StackBias ub{};
+                memcpy(ub.v, sb.data() + LU::oBias, sizeof ub.v);
+                e->upd_bias.push_back(ub);
             }
             if (cudaMalloc(&e->stack_upd_blobs[it], sb.size()) != cudaSuccess ||
                 cudaMemcpy(e->stack_upd_blobs[it], sb.data(), sb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -672,6 +720,8 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
     acc(set_smem(nrx_stack_tm_kernel, TmSmem::kTotal));
+    acc(set_smem(nrx_stack_ws_kernel<kStackInit>, WsSmem<kStackInit>::kTotal));
+    acc(set_smem(nrx_stack_ws_kernel<kStackUpdate>, WsSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
     NRX_CUDA(cudaDeviceSynchronize());
     *out = e;
@@ -715,8 +765,8 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    if (fused < 0 || fused > 4) return fail(NRX_ERR_INVALID, "fused must be 0 ... 4");
-    if (fused == 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plan 4 needs cuTensorMapEncodeTiled (driver entry point not found)");
+    if (fused < 0 || fused > 5) return fail(NRX_ERR_INVALID, "fused must be 0 ... 5");
+    if (fused >= 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plan 4 needs cuTensorMapEncodeTiled (driver entry point not found)");
     e->fused = fused;
     return NRX_OK;
 }
@@ -859,7 +909,10 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             kp.active_tx = active_tx + size_t(b0) * U;
             kp.pair_agg = 0;
             kp.sp_out = pair ? sp_cur : nullptr;
-            {
+            const bool piped = e->fused == 5;           // plan 5: warp-specialised pipelined stack kernels
+            if (piped && !io_index) {                   // (per-user StateInit stacks, Var-IO: the serial kernel switches weights per item)
+                if (const int rc = launch_stack_ws<kStackInit>(e, st, kp, BU, F, e->init_bias[llr_head].v)) return rc;
+            } else {
                 Timed t(e, st, NRX_K_STACK_INIT);
                 if (pair) nrx_stack_kernel<kStackInit, true><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
                 else if (cta_pair && !io_index) {
@@ -880,6 +933,8 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
                 if (e->fused == 4) {
                     const int rc = launch_stack_tm(e, st, it, kp.a_in, kp.s_in, kp.s_out, BU, F);
                     if (rc) return rc;
+                } else if (piped) {
+                    if (const int rc = launch_stack_ws<kStackUpdate>(e, st, kp, BU, F, e->upd_bias[it].v)) return rc;
                 } else {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
@@ -1048,6 +1103,12 @@ int nrx_debug_phase_cycles(unsigned long long* out32) {
     unsigned long long zero[32] = {0};
     if (cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    return NRX_OK;
+}
+int nrx_debug_ws_cycles(unsigned long long* out48) {
+    unsigned long long zero[48] = {0};
+    if (cudaMemcpyFromSymbol(out48, g_ws_cycles, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_ws_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     return NRX_OK;
 }
 int nrx_debug_tm_cycles(unsigned long long* out32) {
