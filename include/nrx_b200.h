@@ -44,18 +44,20 @@ typedef struct nrx_engine nrx_engine;
 /* What CGNN.__init__ / CGNNOFDM.__init__ read from sys_parameters
  * (utils/neural_rx.py:407-530, 638-662) plus the PUSCH grid geometry. */
 typedef struct nrx_model_desc {
-    int32_t num_rx_ant;          /* N_rx (<= 7)                                                     */
-    int32_t max_num_tx;          /* U   (<= NRX_MAX_TX)                                             */
-    int32_t num_subcarriers;     /* F = 12 * n_size_bwp                                             */
-    int32_t num_ofdm_symbols;    /* T (14)                                                          */
-    int32_t d_s;                 /* state width (<= 64; 56 in all shipped configs)                  */
-    int32_t num_it;              /* number of CGNNIt blocks in the weight file                      */
-    int32_t units_init[2];       /* num_units_init   — must be {128,128}                            */
-    int32_t units_agg;           /* num_units_agg[i] — one hidden layer, <= 64                      */
-    int32_t units_state[2];      /* num_units_state[i] — must be {128,128}                          */
-    int32_t units_readout;       /* num_units_readout — one hidden layer of 128                     */
-    int32_t n_io;                /* number of StateInit / ReadoutLLRs stacks in the file            */
-    int32_t io_bits[NRX_MAX_IO]; /* output width of each LLR head (<= 8)                            */
+    int32_t num_rx_ant;          /* N_rx in [1, 7]                                                  */
+    int32_t max_num_tx;          /* U in [1, NRX_MAX_TX]                                            */
+    int32_t num_subcarriers;     /* F = 12 * n_size_bwp: a positive multiple of focc_block          */
+    int32_t num_ofdm_symbols;    /* T: must be 14                                                   */
+    int32_t d_s;                 /* state width: a multiple of 4 in [4, 60] (56 in all shipped configs; two
+                                    more channels of the 64-wide state rows carry the positional encoding)  */
+    int32_t num_it;              /* number of CGNNIt blocks in the weight file (>= 1)               */
+    int32_t units_init[2];       /* num_units_init: two hidden layers, each in [1, 128]             */
+    int32_t units_agg;           /* num_units_agg[i]: one hidden layer in [1, 64]                   */
+    int32_t units_state[2];      /* num_units_state[i]: two hidden layers, each in [1, 128]; the
+                                    same widths in every iteration                                  */
+    int32_t units_readout;       /* num_units_readout: one hidden layer in [1, 128]                 */
+    int32_t n_io;                /* number of StateInit / ReadoutLLRs stacks in the file, [1, NRX_MAX_IO] */
+    int32_t io_bits[NRX_MAX_IO]; /* output width of each LLR head, [1, 16]                          */
     int32_t num_dmrs_symbols;
     int32_t dmrs_symbols[NRX_MAX_DMRS];
     int32_t focc_block;          /* 2 * num_cdm_groups_without_data                                 */
@@ -95,19 +97,16 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  *                         (:184-188) runs in the tail of the preceding stack, each user reads the
  *                         other user's message tensor directly and no aggregation kernel is
  *                         launched (measured on B200: same speed as plan 1);
- *   fused == 3:           as 1, but (two users) the two users of a slot run in the two CTAs of a
- *                         cluster and the pointwise GEMMs are issued for the pair with
- *                         tcgen05.mma.cta_group::2 — each CTA holds half of every weight matrix.
- *                         Bit-identical; measured 31 % slower than plan 1 because the two
- *                         cluster-scope hand-shakes per GEMM sit on the serial chain.  Kept as the
- *                         base of the next kernel generation (ROADMAP.md);
- *   fused == 4:           as 1, but the UpdateState stacks run in the TMEM-resident kernel
- *                         (nrx_stack_tm.cuh: depthwise results written to tensor memory and used
- *                         as the A operand of tcgen05.mma, register line buffers, tensor-map TMA;
- *                         needs cuTensorMapEncodeTiled from the driver).  Bit-identical to plan 1;
- *                         measured 20 % slower per stack launch;
- *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2.
- * All plans compute the same function; the others are kept as cross-checks. */
+ *   fused == 5:           as 1, but the stacks run in the warp-specialised, software-pipelined kernel
+ *                         (nrx_stack_ws.cuh: depthwise warps, an MMA / TMA issuing warp and epilogue
+ *                         warps work on two tiles concurrently; needs cuTensorMapEncodeTiled from
+ *                         the driver).  Bit-identical to plan 1; 2 % faster per 30-slot UpdateState
+ *                         launch on B200;
+ *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2;
+ *   fused == 3, 4:        two measured-slower experiments of round 1 (CTA-pair GEMMs, TMEM-resident
+ *                         stack); only in builds with -DNRX_EXPERIMENTAL_PLANS, otherwise
+ *                         NRX_ERR_UNSUPPORTED.
+ * Plans 0, 1 and 5 are bit-identical; plan 2 differs at fp16 round-off. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);
 
 /* Bytes of device scratch nrx_forward needs for `batch` slots. */
@@ -120,7 +119,8 @@ int nrx_workspace_bytes(const nrx_engine* e, int32_t batch, size_t* bytes);
  *              NULL = stack `llr_head` for every UE (mcs_ue_mask_eval=None, :818-823)
  *   head_index [B][U] int32 or NULL: LLR readout head per UE; NULL = head `llr_head` for every
  *              UE (the reference behaviour: only mcs_arr_eval[0] is evaluated, :847-858)
- *   out_bits   values written per RE (<= 8): io_bits[llr_head] normally, fewer in masking mode
+ *   out_bits   values written per RE, [1, 16]: io_bits[llr_head] normally, fewer in masking mode
+ * io_index / head_index values outside [0, n_io) are clamped on the device (never an out-of-bounds read).
  *   llr / llr_grid / h_hat_refined / h_hat_ls: outputs, any may be NULL (not written).
  * The call neither allocates nor synchronises, so it can be recorded into a CUDA graph with
  * stream capture (batch-1 latency: 98 us replayed vs 124 us eager for nrx_rt on B200).        */
@@ -167,17 +167,10 @@ int nrx_set_host_chunk(nrx_engine* e, int32_t slots);
 /* Number of kernels nrx_forward enqueues for `batch` slots with the current settings. */
 int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launches);
 
-/* Host-only planning helpers (pure functions, no device needed; exported for tests and tooling).
- *   nrx_plan_stack_chunks: plans 1-3 cut every (slot, user) plane of `num_subcarriers` into that many chunks of
- *                          consecutive subcarriers (one work item each; minimises waves x steps on num_sms CTAs);
- *   nrx_plan_stack_jobs:   plan 4 cuts a plane into jobs; eight jobs form one item that a CTA advances in lock step
- *                          for steps_per_item steps (longest job + 6 pipeline-fill steps);
- *   nrx_fragment_column:   physical accumulator column in which plan 4's weight images keep output channel
- *                          `channel` (the 16x256b tcgen05 fragment order; a permutation inside every 16 channels). */
+/* Host-only planning helper (pure function, no device needed; exported for tests and tooling): the stack kernels
+ * cut every (slot, user) plane of `num_subcarriers` into that many chunks of consecutive subcarriers (one work
+ * item each; minimises waves x steps on num_sms persistent CTAs). */
 int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* chunks_per_plane);
-int nrx_plan_stack_jobs(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* jobs_per_plane, int32_t* num_items,
-                        int32_t* steps_per_item);
-int nrx_fragment_column(int32_t channel);
 
 /* Algorithmic multiply-accumulates per user resource element for head `llr_head` at the current
  * num_it (sum of weight elements, biases excluded — SURVEY.md App. A.6). */

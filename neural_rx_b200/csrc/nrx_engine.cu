@@ -17,8 +17,10 @@
 #include "../../include/nrx_b200.h"
 #include "nrx_kernels.cuh"
 #include "nrx_stack.cuh"
+#ifdef NRX_EXPERIMENTAL_PLANS
 #include "nrx_stack_pair.cuh"
 #include "nrx_stack_tm.cuh"
+#endif
 #include "nrx_stack_ws.cuh"
 
 using namespace nrx;
@@ -96,11 +98,13 @@ struct nrx_engine {
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
     struct StackBias { float v[320]; };             // host copies of the stack biases [128 | 128 | 64]: kernel parameters of
     std::vector<StackBias> init_bias, upd_bias;     //   the pipelined stack kernel (per StateInit stack / per iteration)
+#ifdef NRX_EXPERIMENTAL_PLANS
     uint8_t* pair_init_blob = nullptr;              // CTA-pair kernels: [n_io][2 ranks] half-weight images
     std::vector<uint8_t*> pair_upd_blobs;           // [it] -> [2 ranks]
     struct TmConsts { uint32_t tap[3][64][9]; float bias[320]; };
     std::vector<TmConsts> tm_consts;                // [it] taps / biases of the TMEM-resident stack kernel (plan 4)
     std::vector<uint8_t*> tm_blobs;                 // [it] its pointwise B images (output channels in fragment order)
+#endif
     int fused = 1;                                  // 4: TMEM-resident UpdateState stacks (nrx_stack_tm.cuh);
                                                     // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
                                                     // MLP in their tail (two users only), 3: CTA-pair stack kernels
@@ -119,6 +123,7 @@ struct nrx_engine {
     // per-kernel event timing (nrx_set_profiling)
     bool profiling = false;
     struct Span { int cls; cudaEvent_t a, b; };
+    static constexpr size_t kMaxSpans = 1 << 16;    // launches recorded between two nrx_get_profile calls
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     // host-call staging (nrx_forward_host)
@@ -151,8 +156,10 @@ Workspace layout(const nrx_engine* e, int batch) {
     size_t off = 0;
     w.partial = off; off = align_up(off + size_t(batch) * kPowerParts * 4, 256);
     w.z0 = off;      off = align_up(off + P * 32 * 2, 256);
-    w.h1 = off;      off = align_up(off + P * 128 * 2, 256);
-    w.h2 = off;      off = align_up(off + P * 128 * 2, 256);
+    // hidden activations exist in HBM only in the layer-per-kernel plan; the fused plans keep them on chip
+    const size_t hid = e->fused == 0 ? P * 128 * 2 : 0;
+    w.h1 = off;      off = align_up(off + hid, 256);
+    w.h2 = off;      off = align_up(off + hid, 256);
     w.abuf = off;    off = align_up(off + P * 64 * 2, 256);
     w.sbuf = off;    off = align_up(off + P * 64 * 2, 256);
     w.sbuf2 = off;   off = align_up(off + P * 64 * 2, 256);
@@ -214,6 +221,7 @@ void pack_stack_agg(uint8_t* b, const float* const* arrays, int first, int d_s, 
     for (int n = 0; n < d_s; ++n) bias[64 + n] = arrays[first + 3][n];
 }
 
+#ifdef NRX_EXPERIMENTAL_PLANS
 // Per-rank weight image of the CTA-pair stack kernel (StackPairSmem<MODE>): rank r holds output channels
 // [r*N/2, (r+1)*N/2) of every pointwise matrix (rows of the B image), all taps and all biases.
 template <int MODE>
@@ -238,6 +246,8 @@ void pack_stack_pair_blob(uint8_t* b, int rank, const float* const* arrays, int 
         for (int n = 0; n < cout; ++n) bias[n] = arrays[i + 2][n];
     }
 }
+
+#endif
 
 template <int MODE>
 int pack_stack_blob(uint8_t* b, const float* const* arrays, const int64_t* sizes, int first, const int (&widths)[4],
@@ -278,7 +288,11 @@ struct Timed {
     cudaEvent_t a = nullptr, b = nullptr;
     int cls;
     Timed(nrx_engine* e_, cudaStream_t st_, int cls_) : e(e_), st(st_), cls(cls_) {
-        if (e->profiling) {
+        // no timing events inside a stream capture (they would become graph nodes), and a bounded record: a caller
+        // that never collects the profile must not grow it without limit
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (e->profiling && e->spans.size() < nrx_engine::kMaxSpans &&
+            cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
             a = take_event(e);
             b = take_event(e);
             cudaEventRecord(a, st);
@@ -387,6 +401,7 @@ int launch_stack_ws(nrx_engine* e, cudaStream_t st, StackParams kp, int planes, 
     return NRX_OK;
 }
 
+#ifdef NRX_EXPERIMENTAL_PLANS
 // plan 4: one TMEM-resident UpdateState stack launch
 int launch_stack_tm(nrx_engine* e, cudaStream_t st, int it, const __half* a_in, const __half* s_in, __half* s_out, int planes, int F) {
     TmParams tp{};
@@ -408,6 +423,8 @@ int launch_stack_tm(nrx_engine* e, cudaStream_t st, int it, const __half* a_in, 
     return NRX_OK;
 }
 
+#endif
+
 }  // namespace
 
 extern "C" {
@@ -425,9 +442,11 @@ int nrx_destroy(nrx_engine* e) {
     cudaFree(e->readout_blob);
     cudaFree(e->stack_init_blob);
     for (auto* b : e->stack_upd_blobs) cudaFree(b);
+#ifdef NRX_EXPERIMENTAL_PLANS
     for (auto* b : e->tm_blobs) cudaFree(b);
     cudaFree(e->pair_init_blob);
     for (auto* b : e->pair_upd_blobs) cudaFree(b);
+#endif
     cudaFree(e->nn_index);
     cudaFree(e->focc);
     cudaFree(e->pos_enc);
@@ -522,6 +541,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
         if (cudaMalloc(&e->stack_init_blob, host.size()) != cudaSuccess ||
             cudaMemcpy(e->stack_init_blob, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading StateInit stack weights failed"));
+#ifdef NRX_EXPERIMENTAL_PLANS
         using PI = StackPairSmem<kStackInit>;
         std::vector<uint8_t> ph(size_t(PI::kBlob) * d.n_io * 2, 0);
         for (int m = 0; m < d.n_io; ++m)
@@ -531,6 +551,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
         if (cudaMalloc(&e->pair_init_blob, ph.size()) != cudaSuccess ||
             cudaMemcpy(e->pair_init_blob, ph.data(), ph.size(), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading StateInit pair weights failed"));
+#endif
     }
 
     // ---- iterations -----------------------------------------------------------------------------
@@ -541,7 +562,9 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     e->upd_layers.resize(d.num_it);
     e->agg_blobs.resize(d.num_it, nullptr);
     e->stack_upd_blobs.resize(d.num_it, nullptr);
+#ifdef NRX_EXPERIMENTAL_PLANS
     e->pair_upd_blobs.resize(d.num_it, nullptr);
+#endif
     for (int it = 0; it < d.num_it; ++it) {
         if (weight_sizes[idx] != int64_t(d.d_s) * d.units_agg || weight_sizes[idx + 1] != d.units_agg ||
             weight_sizes[idx + 2] != int64_t(d.units_agg) * d.d_s || weight_sizes[idx + 3] != d.d_s)
@@ -561,6 +584,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             std::vector<uint8_t> sb(LU::kBlob, 0);
             rc = pack_stack_blob<kStackUpdate>(sb.data(), weight_arrays, weight_sizes, idx, widths_u, upd_map);
             if (rc) return bail(rc);
+#ifdef NRX_EXPERIMENTAL_PLANS
             {   // plan 4: the same taps as half2 per channel pair and the biases, passed as kernel parameters
                 nrx_engine::TmConsts tc{};
                 const int t_off[3] = {LU::oTap1, LU::oTap2, LU::oTap3};
@@ -590,6 +614,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                     return bail(fail(NRX_ERR_CUDA, "uploading plan-4 stack weights failed"));
                 e->tm_blobs.push_back(dev);
             }
+#endif
             if (it + 1 < d.num_it) {     // message MLP of the next iteration (4 agg + 9 sep-conv arrays per iteration)
                 const int an = idx + 9;
                 if (weight_sizes[an] != int64_t(d.d_s) * d.units_agg || weight_sizes[an + 2] != int64_t(d.units_agg) * d.d_s)
@@ -604,6 +629,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             if (cudaMalloc(&e->stack_upd_blobs[it], sb.size()) != cudaSuccess ||
                 cudaMemcpy(e->stack_upd_blobs[it], sb.data(), sb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(NRX_ERR_CUDA, "uploading UpdateState stack weights failed"));
+#ifdef NRX_EXPERIMENTAL_PLANS
             using PU = StackPairSmem<kStackUpdate>;
             std::vector<uint8_t> pb(size_t(PU::kBlob) * 2, 0);
             for (int r = 0; r < 2; ++r)
@@ -611,6 +637,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
             if (cudaMalloc(&e->pair_upd_blobs[it], pb.size()) != cudaSuccess ||
                 cudaMemcpy(e->pair_upd_blobs[it], pb.data(), pb.size(), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(NRX_ERR_CUDA, "uploading UpdateState pair weights failed"));
+#endif
         }
         e->upd_layers[it].resize(3);
         for (int l = 0; l < 3; ++l) {
@@ -715,15 +742,20 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_readout_kernel, kRoSmem));
     acc(set_smem(nrx_stack_kernel<kStackInit, false>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, false>, StackSmem<kStackUpdate>::kTotal));
+#ifdef NRX_EXPERIMENTAL_PLANS
     acc(set_smem(nrx_stack_pair_kernel<kStackInit>, StackPairSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_pair_kernel<kStackUpdate>, StackPairSmem<kStackUpdate>::kTotal));
+#endif
     acc(set_smem(nrx_stack_kernel<kStackInit, true>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, true>, StackSmem<kStackUpdate>::kTotal));
+#ifdef NRX_EXPERIMENTAL_PLANS
     acc(set_smem(nrx_stack_tm_kernel, TmSmem::kTotal));
+#endif
     acc(set_smem(nrx_stack_ws_kernel<kStackInit>, WsSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_ws_kernel<kStackUpdate>, WsSmem<kStackUpdate>::kTotal));
     if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)));
-    NRX_CUDA(cudaDeviceSynchronize());
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return bail(fail(NRX_ERR_CUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(ce)));
     *out = e;
     return NRX_OK;
 }
@@ -766,6 +798,10 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
     if (fused < 0 || fused > 5) return fail(NRX_ERR_INVALID, "fused must be 0 ... 5");
+#ifndef NRX_EXPERIMENTAL_PLANS
+    if (fused == 3 || fused == 4)
+        return fail(NRX_ERR_UNSUPPORTED, "plans 3 and 4 are experiments that are not in the default build (-DNRX_EXPERIMENTAL_PLANS)");
+#endif
     if (fused >= 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plan 4 needs cuTensorMapEncodeTiled (driver entry point not found)");
     e->fused = fused;
     return NRX_OK;
@@ -798,6 +834,7 @@ int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_s
     *chunks_per_plane = choose_chunks(planes, num_subcarriers, num_sms);
     return NRX_OK;
 }
+#ifdef NRX_EXPERIMENTAL_PLANS
 int nrx_plan_stack_jobs(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* jobs_per_plane, int32_t* num_items,
                         int32_t* steps_per_item) {
     if (planes < 1 || num_subcarriers < 1 || num_sms < 1 || !jobs_per_plane || !num_items || !steps_per_item)
@@ -809,6 +846,8 @@ int nrx_plan_stack_jobs(int32_t planes, int32_t num_subcarriers, int32_t num_sms
     return NRX_OK;
 }
 int nrx_fragment_column(int32_t channel) { return channel < 0 ? -1 : tm_phys_col(channel); }
+
+#endif
 
 int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs) {
     if (!e || !macs || llr_head < 0 || llr_head >= e->d.n_io) return fail(NRX_ERR_INVALID, "nrx_mac_per_pixel: bad argument");
@@ -887,6 +926,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             __half* s_alt = reinterpret_cast<__half*>(ws + w.sbuf2);
             StackParams kp{};
             kp.F = F; kp.U = U; kp.d_s = d.d_s;
+            kp.n_stacks = d.n_io;
             kp.n_chunks = choose_chunks(BU, F, e->num_sms);
             kp.num_items = kp.n_chunks * BU;
             kp.pos_enc = pe_tab;
@@ -894,12 +934,14 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
             // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
             const bool pair = U == 2 && e->fused == 2;
+#ifdef NRX_EXPERIMENTAL_PLANS
             // plan 3: CTA-pair stack kernels (two users, one stack for both users of a slot)
             const bool cta_pair = U == 2 && e->fused == 3;
             StackParams kq = kp;                        // geometry of the pair launches: items = (slot, chunk)
-            kq.n_chunks = choose_chunks(bp, F, e->num_sms / 2);
+            kq.n_chunks = choose_chunks(bp, F, e->num_sms / 2 > 0 ? e->num_sms / 2 : 1);
             kq.num_items = kq.n_chunks * bp;
             const int pgrid = 2 * (kq.num_items < e->num_sms / 2 ? kq.num_items : e->num_sms / 2);
+#endif
             __half* sp_cur = abuf;
             __half* sp_alt = reinterpret_cast<__half*>(ws + w.abuf2);
             kp.z0 = z0; kp.s_out = s_cur;
@@ -915,14 +957,18 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             } else {
                 Timed t(e, st, NRX_K_STACK_INIT);
                 if (pair) nrx_stack_kernel<kStackInit, true><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+#ifdef NRX_EXPERIMENTAL_PLANS
                 else if (cta_pair && !io_index) {
                     kq.z0 = kp.z0; kq.s_out = kp.s_out; kq.wblob = e->pair_init_blob; kq.stack_index = nullptr;
                     kq.default_stack = llr_head; kq.active_tx = kp.active_tx; kq.pair_agg = 0; kq.sp_out = nullptr;
                     nrx_stack_pair_kernel<kStackInit><<<pgrid, kStackThreads, StackPairSmem<kStackInit>::kTotal, st>>>(kq);
-                } else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+                }
+#endif
+                else nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
             }
             kp.stack_index = nullptr;
             kp.default_stack = 0;
+            kp.n_stacks = 1;
             kp.pair_agg = pair ? 1 : 0;
             for (int it = 0; it < e->num_it; ++it) {
                 if (!pair)
@@ -930,19 +976,25 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
                 kp.a_in = pair ? sp_cur : abuf; kp.s_in = s_cur; kp.s_out = s_alt;
                 kp.sp_out = pair && it + 1 < e->num_it ? sp_alt : nullptr;
                 kp.wblob = e->stack_upd_blobs[it];
+#ifdef NRX_EXPERIMENTAL_PLANS
                 if (e->fused == 4) {
                     const int rc = launch_stack_tm(e, st, it, kp.a_in, kp.s_in, kp.s_out, BU, F);
                     if (rc) return rc;
-                } else if (piped) {
+                } else
+#endif
+                if (piped) {
                     if (const int rc = launch_stack_ws<kStackUpdate>(e, st, kp, BU, F, e->upd_bias[it].v)) return rc;
                 } else {
                     Timed t(e, st, NRX_K_STACK_UPD);
                     if (pair) nrx_stack_kernel<kStackUpdate, true><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+#ifdef NRX_EXPERIMENTAL_PLANS
                     else if (cta_pair) {
                         kq.a_in = kp.a_in; kq.s_in = kp.s_in; kq.s_out = kp.s_out; kq.wblob = e->pair_upd_blobs[it];
                         kq.stack_index = nullptr; kq.default_stack = 0; kq.pair_agg = 0; kq.sp_out = nullptr;
                         nrx_stack_pair_kernel<kStackUpdate><<<pgrid, kStackThreads, StackPairSmem<kStackUpdate>::kTotal, st>>>(kq);
-                    } else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+                    }
+#endif
+                    else nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
                 }
                 __half* tmp = s_cur; s_cur = s_alt; s_alt = tmp;
                 tmp = sp_cur; sp_cur = sp_alt; sp_alt = tmp;
@@ -950,6 +1002,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
         } else {
             SepParams sp{};
             sp.F = F; sp.U = U; sp.d_s = d.d_s;
+            sp.n_stacks = d.n_io;
             sp.tiles_per_bu = (F + kTileF - 1) / kTileF;
             sp.num_tiles = sp.tiles_per_bu * BU;
             sp.pos_enc = pe_tab;
@@ -968,6 +1021,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             // ---- CGNN iterations (:576-593) --------------------------------------------------------
             sp.stack_index = nullptr;
             sp.default_stack = 0;
+            sp.n_stacks = 1;
             for (int it = 0; it < e->num_it; ++it) {
                 if (const int rc = launch_agg(e, st, sbuf, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp)) return rc;
                 const auto& L = e->upd_layers[it];
@@ -998,6 +1052,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
         rp.tiles_per_bu = (per_slot + 127) / 128;
         rp.num_tiles = rp.tiles_per_bu * BU;
         rp.default_head = llr_head;
+        rp.n_heads = d.n_io;
         rp.vec = ((reinterpret_cast<uintptr_t>(rp.llr) | reinterpret_cast<uintptr_t>(rp.llr_grid) |
                    reinterpret_cast<uintptr_t>(rp.h_ref)) & 15u) == 0;
         const int grid = rp.num_tiles < e->num_sms ? rp.num_tiles : e->num_sms;
@@ -1111,12 +1166,14 @@ int nrx_debug_ws_cycles(unsigned long long* out48) {
     if (cudaMemcpyToSymbol(g_ws_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     return NRX_OK;
 }
+#ifdef NRX_EXPERIMENTAL_PLANS
 int nrx_debug_tm_cycles(unsigned long long* out32) {
     unsigned long long zero[32] = {0};
     if (cudaMemcpyFromSymbol(out32, g_tm_cycles, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     if (cudaMemcpyToSymbol(g_tm_cycles, zero, sizeof zero) != cudaSuccess) return NRX_ERR_CUDA;
     return NRX_OK;
 }
+#endif
 #endif
 
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {

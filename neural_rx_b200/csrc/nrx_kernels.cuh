@@ -251,6 +251,7 @@ struct SepParams {
     int F, U, d_s;
     int tiles_per_bu, num_tiles;
     int default_stack;
+    int n_stacks;              // stacks in wblob: stack_index values are clamped to [0, n_stacks)
     uint32_t blob_bytes;
 };
 
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 2) nrx_sepconv_kernel(SepParams p) {
         const int bu = tile / p.tiles_per_bu, ft = tile - bu * p.tiles_per_bu;
         const int f0 = ft * kTileF;
         const int valid_rows = min(kTileF, p.F - f0) * kT;
-        const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
+        const int stack = min(max(p.stack_index ? p.stack_index[bu] : p.default_stack, 0), p.n_stacks - 1);
         if (stack != loaded_stack) {                 // block-uniform; first tile or Var-IO switch
             __syncthreads();                         // nobody still reads the old taps / bias
             if (tid == 0) {
@@ -707,6 +708,7 @@ struct ReadoutParams {
     float* llr_aerial;           // [Bp][out_bits][U][F][T] = -LLR (NeuralReceiverONNX, :1809-1810) or null
     int F, U, N2, out_bits, n_data;
     int rows_per_bu, tiles_per_bu, num_tiles, default_head;
+    int n_heads;                 // heads in wblob: head_index values are clamped to [0, n_heads)
     int vec;                     // output pointers are 16-byte aligned: vector stores
 };
 
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
         const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
-        const int head = p.head_index ? p.head_index[bu] : p.default_head;
+        const int head = min(max(p.head_index ? p.head_index[bu] : p.default_head, 0), p.n_heads - 1);
         if (head != loaded_head) {
             __syncthreads();
             if (tid == 0) {

@@ -52,7 +52,14 @@ struct StackParams {
     int F, U, d_s;
     int n_chunks, num_items;
     int default_stack;
+    int n_stacks;                // stacks in wblob: stack_index values are clamped to [0, n_stacks)
 };
+
+// per-plane stack (Var-IO) with the index clamped into the weight image: the index arrays come straight from the caller
+__device__ __forceinline__ int stack_of(const StackParams& p, int bu) {
+    const int s = p.stack_index ? p.stack_index[bu] : p.default_stack;
+    return min(max(s, 0), p.n_stacks - 1);
+}
 
 __host__ __device__ constexpr int align_up_c(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
         const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
-        const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
+        const int stack = stack_of(p, bu);
         if (stack != loaded_stack) {                   // block-uniform: first item or Var-IO switch
             if (MLP && pend) {                         // the pending MLP still reads the resident weights
                 mlp_hidden();
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             } else if (item + int(gridDim.x) < p.num_items) {   // last step: first window of the CTA's next item
                 const int nitem = item + int(gridDim.x);
                 const int nbu = nitem / p.n_chunks, ncj = nitem - nbu * p.n_chunks;
-                const int nstack = p.stack_index ? p.stack_index[nbu] : p.default_stack;
+                const int nstack = stack_of(p, nbu);
                 if (nstack == loaded_stack) {
                     const int nbu_a = p.pair_agg ? (nbu ^ 1) : nbu;
                     const bool na_live = !p.pair_agg || p.active_tx[nbu_a] != 0.f;

@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStackThreads, 1) nr
         const int bu = slot * 2 + int(rank);
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
-        const int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;   // host guarantees: same for both users
+        const int stack = stack_of(p, bu);   // host guarantees: same for both users
         if (stack != loaded_stack) {
             __syncthreads();
             if (tid == 0) {
@@ -273,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStackThreads, 1) nr
                 const int nitem = item + n_clusters;
                 const int nslot = nitem / p.n_chunks, ncj = nitem - nslot * p.n_chunks;
                 const int nbu = nslot * 2 + int(rank);
-                const int nstack = p.stack_index ? p.stack_index[nbu] : p.default_stack;
+                const int nstack = stack_of(p, nbu);
                 if (nstack == loaded_stack) {
                     stage_z_of(nbu, int((long long)ncj * p.F / p.n_chunks) - kRunIn + 1);
                     z_prefetched = true;

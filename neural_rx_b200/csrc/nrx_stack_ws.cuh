@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) nrx_stack_ws_kernel(const __gri
         const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
         const int K = (c1 - c0 + kWsRunIn + kWsStepF - 1) / kWsStepF;
-        int stack = p.stack_index ? p.stack_index[bu] : p.default_stack;
-        stack = stack < 0 ? 0 : stack;                  // (range-checked on the host; never index outside the image)
+        const int stack = stack_of(p, bu);
         __syncthreads();                                // B1: every role has finished the previous item
         if (stack != loaded_stack) {
             const uint8_t* blob = p.wblob + size_t(stack) * G::kBlob;

@@ -24,7 +24,7 @@ NRX_MAX_DMRS = 4
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
-    "nrx_plan_stack_chunks", "nrx_plan_stack_jobs", "nrx_fragment_column",
+    "nrx_plan_stack_chunks",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
 )
 
@@ -92,9 +92,6 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     i32o = ctypes.POINTER(ctypes.c_int32)
     lib.nrx_plan_stack_chunks.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i32o]
-    lib.nrx_plan_stack_jobs.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i32o, i32o, i32o]
-    lib.nrx_fragment_column.argtypes = [ctypes.c_int32]
-    lib.nrx_fragment_column.restype = ctypes.c_int32
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_get_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
@@ -195,9 +192,8 @@ class NrxEngine:
 
     def set_fused(self, fused) -> None:
         """1/True: fused stack kernels + aggregation kernel (default); 2: fused stacks with the
-        message MLP in their tail (two users); 3: CTA-pair stack kernels (cta_group::2 GEMMs, half the
-        weights per CTA; experimental); 4: TMEM-resident UpdateState stacks (experimental); 0/False: one kernel
-        per SeparableConv2D layer."""
+        message MLP in their tail (two users); 5: warp-specialised pipelined stack kernels; 0/False: one kernel
+        per SeparableConv2D layer (3, 4: round-1 experiments, only in -DNRX_EXPERIMENTAL_PLANS builds)."""
         self._check(self._lib.nrx_set_fused(self._h, int(fused)))
 
     def set_host_chunk(self, slots: int) -> None:
@@ -243,10 +239,15 @@ class NrxEngine:
     # ---- device call (torch tensors) ------------------------------------------------------------
     def forward(self, y, active_tx, io_index=None, head_index=None, llr_head: int = 0,
                 out_bits: Optional[int] = None, want: Sequence[str] = ("llr", "h_hat_refined", "h_hat"),
-                out: Optional[Dict] = None, stream=None) -> Dict:
+                out: Optional[Dict] = None, stream=None, workspace=None) -> Dict:
         """``y`` complex64 CUDA tensor [B,1,N_rx,T,F]; ``active_tx`` float32 CUDA [B,U];
         ``io_index`` / ``head_index`` int32 CUDA [B,U] or None.  Enqueues on the current stream
-        and returns CUDA tensors (keys of ``want`` among llr, llr_grid, h_hat_refined, h_hat)."""
+        and returns CUDA tensors (keys of ``want`` among llr, llr_grid, h_hat_refined, h_hat).
+
+        Scratch memory: ``workspace`` (a uint8 CUDA tensor of at least ``workspace_bytes(B)`` bytes) or, by
+        default, one engine-owned tensor that grows on demand and is shared by all calls — so calls of one engine
+        must be issued on ONE stream at a time (two forwards in flight on different streams would race on it;
+        pass distinct ``workspace`` tensors for that)."""
         import torch
 
         g, N = self.grid, self.cfg.num_rx_antennas
@@ -272,8 +273,14 @@ class NrxEngine:
             if k not in res:
                 res[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
         need = self.workspace_bytes(B)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if workspace is not None:
+            if workspace.dtype != torch.uint8 or not workspace.is_cuda or workspace.numel() < need:
+                raise ValueError(f"workspace must be a uint8 CUDA tensor of at least {need} bytes")
+            ws = workspace
+        else:
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._ws
         ptr = lambda k: res[k].data_ptr() if k in want else None
         iptr = lambda t: None if t is None else t.to(dtype=torch.int32).contiguous()
         io_t, head_t = iptr(io_index), iptr(head_index)
@@ -282,8 +289,8 @@ class NrxEngine:
             self._h, ctypes.c_void_p(st), B, y.data_ptr(), active_tx.data_ptr(),
             None if io_t is None else io_t.data_ptr(), None if head_t is None else head_t.data_ptr(),
             int(llr_head), bits, ptr("llr"), ptr("llr_grid"), ptr("h_hat_refined"), ptr("h_hat"),
-            self._ws.data_ptr(), self._ws.numel()))
-        res["_keepalive"] = (y, active_tx, io_t, head_t)
+            ws.data_ptr(), ws.numel()))
+        res["_keepalive"] = (y, active_tx, io_t, head_t, ws)
         del per
         return res
 
@@ -293,11 +300,18 @@ class NrxEngine:
         """Capture one forward on the given (static) input tensors into a CUDA graph.  nrx_forward
         only enqueues kernels (no allocation, no synchronisation), so it can be recorded as is.
         Returns ``(graph, outputs)``: overwrite ``y`` / ``active_tx`` in place, call ``graph.replay()``
-        and read ``outputs`` (same tensors every time)."""
+        and read ``outputs`` (same tensors every time).
+
+        The graph bakes device addresses in (inputs, outputs, scratch, tensor maps encoded from the scratch
+        address), so it gets a workspace tensor of its own that lives as long as the graph object does
+        (``graph._nrx_keepalive``) — later eager calls that grow or drop the engine's shared workspace, or
+        ``set_slots_per_pass``, cannot pull memory from under a replay."""
         import torch
 
         outs: Dict = {}
-        kw = dict(io_index=io_index, head_index=head_index, llr_head=llr_head, out_bits=out_bits, want=want, out=outs)
+        ws = torch.empty(self.workspace_bytes(int(y.shape[0])), dtype=torch.uint8, device=y.device)
+        kw = dict(io_index=io_index, head_index=head_index, llr_head=llr_head, out_bits=out_bits, want=want, out=outs,
+                  workspace=ws)
         side = torch.cuda.Stream(device=y.device)
         side.wait_stream(torch.cuda.current_stream(y.device))
         with torch.cuda.stream(side):
@@ -306,6 +320,7 @@ class NrxEngine:
             with torch.cuda.graph(graph, stream=side):
                 self.forward(y, active_tx, **kw)
         torch.cuda.current_stream(y.device).wait_stream(side)
+        graph._nrx_keepalive = (ws, outs.get("_keepalive"), dict(outs))
         return graph, {k: v for k, v in outs.items() if not k.startswith("_")}
 
     # ---- Aerial / TensorRT-shaped call (NeuralReceiverONNX.forward, utils/neural_rx.py:1773-1812) ----

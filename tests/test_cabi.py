@@ -47,11 +47,9 @@ def test_argument_validation_without_device(lib):
 
 @pytest.mark.parametrize("planes,F", [(60, 1584), (2, 1584), (2, 48), (7, 12), (14, 132), (120, 3276)])
 def test_stack_work_split_without_device(lib, planes, F):
-    """Host-only planning helpers: how the stack kernels cut the subcarrier axis over 148 CTAs.
-    Plans 1-3: chunks of a plane are a partition of [0, F) (c_j = j*F/n) and fill the machine;
-    plan 4: jobs (eight per item, advanced in lock step) cover every subcarrier once, the step count
-    is the longest job plus the six pipeline-fill steps, and the chosen split is never worse than
-    one job per plane."""
+    """Host-only planning helper: how the stack kernels cut the subcarrier axis over 148 CTAs: the chunks of a
+    plane are a partition of [0, F) (c_j = j*F/n), every chunk has at least 5 subcarriers and the chosen count
+    minimises waves x steps-per-item (9-subcarrier steps, 4-subcarrier run-in)."""
     sms = 148
     n = ctypes.c_int32()
     assert lib.nrx_plan_stack_chunks(planes, F, sms, ctypes.byref(n)) == 0
@@ -60,29 +58,8 @@ def test_stack_work_split_without_device(lib, planes, F):
     edges = [j * F // n for j in range(n + 1)]
     assert edges[0] == 0 and edges[-1] == F and all(b > a for a, b in zip(edges, edges[1:]))
 
-    j, items, steps = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    assert lib.nrx_plan_stack_jobs(planes, F, sms, ctypes.byref(j), ctypes.byref(items), ctypes.byref(steps)) == 0
-    j, items, steps = j.value, items.value, steps.value
-    assert 1 <= j <= F
-    bounds = [i * F // j for i in range(j + 1)]
-    lens = [b - a for a, b in zip(bounds, bounds[1:])]
-    assert sum(lens) == F and min(lens) >= 1
-    assert steps == max(lens) + 6 == -(-F // j) + 6
-    assert items == -(-planes * j // 8)
-
-    def cost(jj):
-        it = -(-planes * jj // 8)
-        return -(-it // sms) * (-(-F // jj) + 6)
-    assert cost(j) <= cost(1) and cost(j) == min(cost(jj) for jj in range(1, min(F, 1024) + 1))
-    assert lib.nrx_plan_stack_jobs(0, F, sms, None, None, None) == 1       # NRX_ERR_INVALID
-
-
-def test_fragment_column_order(lib):
-    """Plan 4 keeps output channel 16c + 4g + 2e + d in accumulator column 16c + 8e + 2g + d (the columns one
-    thread of the 16x256b tcgen05 fragment owns are four consecutive channels): a permutation of every group of 16."""
-    cols = [lib.nrx_fragment_column(n) for n in range(128)]
-    assert sorted(cols) == list(range(128))
-    for n in range(128):
-        c, g, e, d = n // 16, (n % 16) // 4, (n % 4) // 2, n % 2
-        assert cols[n] == 16 * c + 8 * e + 2 * g + d
-    assert lib.nrx_fragment_column(-1) == -1
+    def cost(nn):
+        steps = -(-(-(-F // nn) + 4) // 9)
+        return -(-planes * nn // sms) * steps
+    assert cost(n) == min(cost(nn) for nn in range(1, min(max(F // 5, 1), 512) + 1))
+    assert lib.nrx_plan_stack_chunks(0, F, sms, None) == 1                 # NRX_ERR_INVALID

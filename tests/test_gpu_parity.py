@@ -117,16 +117,15 @@ def test_fused_equals_layerwise(label, n_prb, batch):
     if cfg.num_mcss_supported > 1:
         kw = dict(io_index=np.tile(np.array([[0, 1]], np.int32), (batch, 1)))
     outs = []
-    for fused in (1, 2, 0, 3, 4):
+    for fused in (1, 2, 0, 5):
         eng = _engine(cfg, weights, grid, fused=fused)
         outs.append(_run(eng, sb, **dict(kw)))
         eng.close()
     for k in ("llr", "llr_grid", "h_hat_refined"):
         assert rel_l2(outs[0][k], outs[2][k]) <= 1e-6, k      # fused stacks vs layer-per-kernel
-        assert rel_l2(outs[3][k], outs[2][k]) <= 1e-6, k      # CTA-pair stack kernels vs layer-per-kernel
-        # plan 4 (TMEM-resident UpdateState stacks, nrx_stack_tm.cuh): register line buffers, A operand in
-        # tensor memory, scatter-form depthwise - same sums in the same order: bit-identical
-        assert np.array_equal(outs[4][k], outs[0][k]), k
+        # plan 5 (warp-specialised pipelined stacks, nrx_stack_ws.cuh): other tiling (8-subcarrier steps, ring
+        # buffers), other thread mapping, other schedule - the same sums in the same order: bit-identical
+        assert np.array_equal(outs[3][k], outs[0][k]), k
         # the two-user fast path takes the other user's message directly instead of forming
         # (sp_0 + sp_1) - sp_u in fp32 (utils/neural_rx.py:196) and rounds sp (not a) to fp16:
         # same function, differences at fp16 round-off level
@@ -137,12 +136,12 @@ def test_fused_equals_layerwise(label, n_prb, batch):
         assert rel_l2(outs[2]["llr"], ref["llr"]) <= TOL_EXACT
 
 
-@pytest.mark.parametrize("label,n_prb,batch", [("nrx_rt", 3, 5), ("nrx_rt", 11, 7), ("nrx_large", 132, 3)])
-def test_tm_plan_job_split(label, n_prb, batch):
-    """Plan 4 cuts every (slot, user) plane into jobs of consecutive subcarriers and runs eight of them
-    in lock step per CTA; odd plane counts and widths leave partially filled items, jobs of unequal
-    length and sequences that start / end at the grid edge (zero padding of every layer).  Results must
-    not depend on the split: identical to plan 1, also with an inactive user."""
+@pytest.mark.parametrize("label,n_prb,batch", [("nrx_rt", 3, 5), ("nrx_rt", 11, 7), ("nrx_large", 132, 3), ("nrx_rt", 273, 1)])
+def test_pipelined_plan_chunk_split(label, n_prb, batch):
+    """Plan 5 cuts every (slot, user) plane into chunks of consecutive subcarriers that a CTA walks in 8-subcarrier
+    steps with a 4-subcarrier run-in; odd plane counts and widths give chunks of unequal length, ragged last steps
+    and chunks that start / end at the grid edge (zero padding of every layer, TMA zero fill of the first
+    window).  Results must not depend on the split: identical to plan 1, also with an inactive user."""
     import torch
     cfg = get_config(label)
     weights, _ = get_weights(cfg)
@@ -151,7 +150,7 @@ def test_tm_plan_job_split(label, n_prb, batch):
     act = np.array(sb.active_tx, copy=True)
     act[0, 1] = 0.0
     outs = []
-    for fused in (1, 4):
+    for fused in (1, 5):
         eng = _engine(cfg, weights, grid, fused=fused)
         out = eng.forward(torch.as_tensor(sb.y).cuda(), torch.as_tensor(act).cuda(), want=("llr", "h_hat_refined"))
         torch.cuda.synchronize()
@@ -164,7 +163,7 @@ def test_tm_plan_job_split(label, n_prb, batch):
 
 @pytest.mark.parametrize("num_tx,ports,active", [(1, [[0]], [[1]]), (3, [[0], [2], [1]], [[1, 1, 1], [1, 0, 1]]),
                                                   (4, [[0], [2], [1], [3]], [[1, 1, 1, 1], [0, 1, 1, 0]])])
-@pytest.mark.parametrize("fused", [1, 0, 4])
+@pytest.mark.parametrize("fused", [1, 0, 5])
 def test_other_user_counts(num_tx, ports, active, fused):
     """1, 3 and 4 users (AggregateUserStates general form: masked sum over the other users and the
     1 / max(n_active - 1, 1) scaling, utils/neural_rx.py:192-204; single-UE shapes).
