@@ -194,6 +194,23 @@ int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);
 int nrx_set_profiling(nrx_engine* e, int32_t enable);
 int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
 
+/* Test hooks: run ONE kernel of the path on caller-provided DEVICE tensors in the engine's internal activation
+ * layout (fp16, one 64-channel row per user resource element, row = ((slot*U + user)*F + f)*14 + t;
+ * state rows = [s (d_s) | pos. encoding (2) | 0]).  They exist so that tests can drive the kernels with
+ * random tensors at edge-case widths against the reference's AggregateUserStates / StateInit / UpdateState /
+ * read-out blocks (utils/neural_rx.py:135-207, 61-132, 210-270, 309-404); the product path does not use them.
+ *   nrx_debug_aggregate: a = AggregateUserStates_it(s, active_tx)
+ *   nrx_debug_stack:     it >= 0: s_out = UpdateState_it(a, s) (residual included);
+ *                        it <  0: s_out = StateInit_stack(z0), z0 rows of 32 channels [y | pe | h_ls | 0]
+ *                        (execution plan 1 or 5 as set by nrx_set_fused)
+ *   nrx_debug_readout:   llr_grid [B][U][F][T][out_bits], h_hat_refined [B][U][F][T][2*N_rx] from s */
+int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t batch, const void* s_f16,
+                        const float* active_tx, void* a_f16);
+int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack, int32_t batch, const void* z0_f16,
+                    const void* a_f16, const void* s_f16, void* s_out_f16);
+int nrx_debug_readout(nrx_engine* e, void* cuda_stream, int32_t head, int32_t batch, int32_t out_bits,
+                      const void* s_f16, float* llr_grid, float* h_hat_refined);
+
 const char* nrx_last_error(void);
 const char* nrx_version(void);
 

@@ -1176,6 +1176,82 @@ int nrx_debug_tm_cycles(unsigned long long* out32) {
 #endif
 #endif
 
+// ---- test hooks: ONE kernel of the path on caller-provided device tensors ----------------------------------------
+// (tests/test_gpu_kernels.py drives them with random tensors at edge-case widths; not used by the product path)
+int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t batch, const void* s_f16, const float* active_tx,
+                        void* a_f16) {
+    if (!e || !s_f16 || !active_tx || !a_f16 || batch < 1 || it < 0 || it >= e->d.num_it)
+        return fail(NRX_ERR_INVALID, "nrx_debug_aggregate: bad argument");
+    NRX_CUDA(cudaSetDevice(e->device));
+    const int rc = launch_agg(e, static_cast<cudaStream_t>(cuda_stream), static_cast<const __half*>(s_f16), static_cast<__half*>(a_f16),
+                              e->agg_blobs[it], active_tx, e->d.max_num_tx, e->d.num_subcarriers * kT, batch);
+    if (rc) return rc;
+    NRX_CUDA(cudaGetLastError());
+    return NRX_OK;
+}
+
+int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack, int32_t batch, const void* z0_f16, const void* a_f16,
+                    const void* s_f16, void* s_out_f16) {
+    if (!e || !s_out_f16 || batch < 1 || it >= e->d.num_it || stack < 0 || stack >= e->d.n_io)
+        return fail(NRX_ERR_INVALID, "nrx_debug_stack: bad argument");
+    const bool init = it < 0;
+    if (init ? !z0_f16 : (!a_f16 || !s_f16)) return fail(NRX_ERR_INVALID, "nrx_debug_stack: null input");
+    if (e->fused != 1 && e->fused != 5) return fail(NRX_ERR_INVALID, "nrx_debug_stack: plans 1 and 5 only");
+    NRX_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const nrx_model_desc& d = e->d;
+    const int F = d.num_subcarriers, BU = batch * d.max_num_tx;
+    StackParams kp{};
+    kp.F = F; kp.U = d.max_num_tx; kp.d_s = d.d_s;
+    kp.n_chunks = choose_chunks(BU, F, e->num_sms);
+    kp.num_items = kp.n_chunks * BU;
+    kp.pos_enc = e->pos_enc;
+    kp.z0 = static_cast<const __half*>(z0_f16);
+    kp.a_in = static_cast<const __half*>(a_f16);
+    kp.s_in = static_cast<const __half*>(s_f16);
+    kp.s_out = static_cast<__half*>(s_out_f16);
+    kp.wblob = init ? e->stack_init_blob : e->stack_upd_blobs[it];
+    kp.default_stack = init ? stack : 0;
+    kp.n_stacks = init ? d.n_io : 1;
+    const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
+    if (e->fused == 5) {
+        const int rc = init ? launch_stack_ws<kStackInit>(e, st, kp, BU, F, e->init_bias[stack].v)
+                            : launch_stack_ws<kStackUpdate>(e, st, kp, BU, F, e->upd_bias[it].v);
+        if (rc) return rc;
+    } else if (init) {
+        nrx_stack_kernel<kStackInit, false><<<sgrid, kStackThreads, StackSmem<kStackInit>::kTotal, st>>>(kp);
+    } else {
+        nrx_stack_kernel<kStackUpdate, false><<<sgrid, kStackThreads, StackSmem<kStackUpdate>::kTotal, st>>>(kp);
+    }
+    NRX_CUDA(cudaGetLastError());
+    return NRX_OK;
+}
+
+int nrx_debug_readout(nrx_engine* e, void* cuda_stream, int32_t head, int32_t batch, int32_t out_bits, const void* s_f16,
+                      float* llr_grid, float* h_hat_refined) {
+    if (!e || !s_f16 || batch < 1 || head < 0 || head >= e->d.n_io || out_bits < 1 || out_bits > 16)
+        return fail(NRX_ERR_INVALID, "nrx_debug_readout: bad argument");
+    NRX_CUDA(cudaSetDevice(e->device));
+    const nrx_model_desc& d = e->d;
+    ReadoutParams rp{};
+    rp.sbuf = static_cast<const __half*>(s_f16);
+    rp.wblob = e->readout_blob;
+    rp.data_index = e->data_index;
+    rp.llr_grid = llr_grid;
+    rp.h_ref = h_hat_refined;
+    rp.F = d.num_subcarriers; rp.U = d.max_num_tx; rp.N2 = 2 * d.num_rx_ant; rp.out_bits = out_bits; rp.n_data = d.num_data_res;
+    rp.rows_per_bu = d.num_subcarriers * kT;
+    rp.tiles_per_bu = (rp.rows_per_bu + 127) / 128;
+    rp.num_tiles = rp.tiles_per_bu * batch * d.max_num_tx;
+    rp.default_head = head;
+    rp.n_heads = d.n_io;
+    rp.vec = ((reinterpret_cast<uintptr_t>(rp.llr_grid) | reinterpret_cast<uintptr_t>(rp.h_ref)) & 15u) == 0;
+    const int grid = rp.num_tiles < e->num_sms ? rp.num_tiles : e->num_sms;
+    nrx_readout_kernel<<<grid, kThreads, kRoSmem, static_cast<cudaStream_t>(cuda_stream)>>>(rp);
+    NRX_CUDA(cudaGetLastError());
+    return NRX_OK;
+}
+
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {
     if (!e || slots < 0) return fail(NRX_ERR_INVALID, "host chunk must be >= 0");
     e->host_chunk = slots;

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
     "nrx_plan_stack_chunks",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
+    "nrx_debug_aggregate", "nrx_debug_stack", "nrx_debug_readout",
 )
 
 KERNEL_CLASSES = ("power", "prep", "sep_32x128", "sep_128x128", "sep_128x64_init_out",
@@ -95,6 +96,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_get_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
+    vp = ctypes.c_void_p
+    lib.nrx_debug_aggregate.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
+    lib.nrx_debug_stack.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
+    lib.nrx_debug_readout.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
     lib.nrx_last_error.restype = ctypes.c_char_p
     lib.nrx_version.restype = ctypes.c_char_p
     for name in EXPORTED_SYMBOLS:
@@ -367,6 +372,41 @@ class NrxEngine:
                                                  ts[2].data_ptr(), ts[3].data_ptr(), ts[4].data_ptr(), llr.data_ptr(),
                                                  h.data_ptr(), self._ws.data_ptr(), self._ws.numel()))
         self._aerial_keepalive = ts
+        return llr, h
+
+    # ---- test hooks: one kernel on tensors in the internal activation layout ------------------------
+    def _stream(self, t):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    def debug_aggregate(self, it: int, s, active_tx):
+        """s: fp16 CUDA [B,U,F,T,64] (state rows) -> a fp16 [B,U,F,T,64]."""
+        import torch
+        s = s.contiguous()
+        act = active_tx.to(dtype=torch.float32).contiguous()
+        a = torch.empty_like(s)
+        self._check(self._lib.nrx_debug_aggregate(self._h, self._stream(s), int(it), int(s.shape[0]), s.data_ptr(),
+                                                  act.data_ptr(), a.data_ptr()))
+        return a
+
+    def debug_stack(self, it: int, batch: int, z0=None, a=None, s=None, stack: int = 0):
+        """it >= 0: UpdateState_it on (a, s) fp16 [B,U,F,T,64]; it < 0: StateInit on z0 fp16 [B,U,F,T,32]."""
+        import torch
+        src = z0 if it < 0 else s
+        out = torch.empty(tuple(src.shape[:-1]) + (64,), dtype=torch.float16, device=src.device)
+        ptr = lambda t: None if t is None else t.contiguous().data_ptr()
+        self._check(self._lib.nrx_debug_stack(self._h, self._stream(src), int(it), int(stack), int(batch), ptr(z0), ptr(a), ptr(s),
+                                              out.data_ptr()))
+        return out
+
+    def debug_readout(self, head: int, s, out_bits: int):
+        import torch
+        s = s.contiguous()
+        B, U, F, T = (int(x) for x in s.shape[:4])
+        llr = torch.empty((B, U, F, T, out_bits), dtype=torch.float32, device=s.device)
+        h = torch.empty((B, U, F, T, 2 * self.cfg.num_rx_antennas), dtype=torch.float32, device=s.device)
+        self._check(self._lib.nrx_debug_readout(self._h, self._stream(s), int(head), B, int(out_bits), s.data_ptr(),
+                                                llr.data_ptr(), h.data_ptr()))
         return llr, h
 
     # ---- host call (NumPy arrays, H2D + D2H inside) --------------------------------------------

@@ -82,8 +82,11 @@ CASES = [
     ("nrx_large", 16, 2, 6.0),
     ("nrx_large", 132, 1, 2.0),    # BASELINE configs[1] geometry
     ("nrx_large_64qam", 24, 2, 9.0),   # configs[3]
+    ("nrx_large_64qam", 132, 1, 8.0),  # configs[3] at full size: 8 iterations, 64-QAM — the case with the least fp16 margin
     ("nrx_large_qpsk", 8, 2, 2.0),
     ("nrx_site_specific_large", 16, 2, 10.0),   # configs[4] (sparse multipath, per-UE power norm)
+    ("nrx_site_specific_large", 132, 1, 6.0),   # configs[4] at full size
+    ("nrx_rt", 273, 1, 8.0),           # widest carrier of the reference's tutorial (273 PRB, F = 3276)
 ]
 
 
@@ -248,6 +251,30 @@ def test_num_it_truncation(label, num_it):
     eng.close()
 
 
+@pytest.mark.parametrize("mask", [[[1, 0], [0, 1]], [[0, 1], [1, 0]]])
+def test_var_mcs_mixed_masks_full_size(mask):
+    """BASELINE configs[2] (nrx_rt_var_mcs) at 132 PRB with the two mixed masks of notebooks/variable_mcs_nrx.ipynb:
+    per-user StateInit stack, each evaluated head against the oracle, and the engine's per-user-heads mode."""
+    from neural_rx_b200.receiver import NeuralPUSCHReceiver
+    cfg = get_config("nrx_rt_var_mcs")
+    weights, _ = get_weights(cfg)
+    grid = build_grid(cfg)
+    mcs_per_ue = [int(np.argmax(m)) for m in mask]
+    sb = make_slots(cfg, grid, batch=1, ebno_db=9.0, seed=45, mcs_per_ue=mcs_per_ue)
+    rx = NeuralPUSCHReceiver(cfg, weights=weights, grid=grid)
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    m = np.asarray(mask, np.float32)[None]
+    for head in (0, 1):
+        out = rx.llrs((sb.y, sb.active_tx), [head], mcs_ue_mask_eval=m, want=("llr", "h_hat_refined"))
+        ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx,
+                                 mcs_arr_eval=(head,), mcs_ue_mask_eval=m)
+        assert out["llr"].shape == ref["llr"].shape == (1, 2, grid.num_data_res * cfg.num_bits_per_symbol[head])
+        assert rel_l2(out["llr"], ref["llr"]) <= TOL_EXACT
+        u = mcs_per_ue.index(head)                       # the user this head was trained for
+        assert sign_agreement(out["llr"][:, u], ref["llr"][:, u]) >= _agree_tol("nrx_rt_var_mcs")
+        assert rel_l2(out["h_hat_refined"], ref["h_hat_refined"]) <= TOL_EXACT
+
+
 @pytest.mark.parametrize("mask", [[[1, 0], [0, 1]], [[0, 1], [1, 0]], [[1, 0], [1, 0]], [[0, 1], [0, 1]]])
 def test_var_mcs_mixed_masks(mask):
     """BASELINE configs[2] (nrx_rt_var_mcs): per-user StateInit stack (one-hot mcs_ue_mask,
@@ -372,6 +399,14 @@ def test_full_size_batch_properties():
     if kind == "shipped":
         ber = uncoded_ber(full["llr"][:3], base.bits, base.active_tx, 4)
         assert ber < 0.08, ber
+    # three distinct slots of the 30-slot run against the oracle (positions 0, 16 and 29 of the batch)
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    ref = O.receiver_forward(net, arch, base.y, grid.pilots, grid.pilot_mask, base.active_tx)
+    for pos in (0, 16, 29):
+        src = pos % 3
+        assert rel_l2(full["llr"][pos], ref["llr"][src]) <= TOL_EXACT, pos
+        assert sign_agreement(full["llr"][pos], ref["llr"][src]) >= _agree_tol("nrx_large"), pos
+        assert rel_l2(full["h_hat_refined"][pos], ref["h_hat_refined"][src]) <= TOL_EXACT, pos
     eng.close()
 
 
@@ -462,4 +497,42 @@ def test_cuda_graph_replay_matches_eager():
         got = outs["llr"].cpu().numpy().copy()
         ref = eng.forward(torch.as_tensor(sb.y[i:i + 1]).cuda(), act, want=("llr",))["llr"].cpu().numpy()
         assert np.array_equal(got, ref)
+    eng.close()
+
+
+BER_CASES = [("nrx_rt", (2.0, 8.0)), ("nrx_large", (0.0, 6.0)), ("nrx_rt_var_mcs", (4.0, 10.0)), ("nrx_large_64qam", (4.0, 10.0)),
+             ("nrx_site_specific_large", (3.0, 12.0))]
+
+
+@pytest.mark.parametrize("label,points", BER_CASES)
+def test_uncoded_ber_and_bmi_match_oracle(label, points):
+    """The five BASELINE configs on the synthetic link (tools/ber_sweep.py as a test): per Eb/N0 point the
+    uncoded BER and the bit-wise mutual information of the engine's LLRs equal the oracle's on the same slots
+    (what can be compared without the third-party TB / LDPC chain), and they improve with SNR."""
+    cfg = get_config(label)
+    weights, kind = get_weights(cfg)
+    grid = build_grid(cfg, n_size_bwp=24)
+    eng = _engine(cfg, weights, grid)
+    arch, net = oracle_arch(cfg), oracle_net(cfg, weights)
+    site = "site_specific" in label
+    bers, bmis = [], []
+    for pi, ebno in enumerate(points):
+        kw = dict(per_ue_power_norm=True, sparse_paths=24) if site else {}
+        sb = make_slots(cfg, grid, batch=3, ebno_db=ebno, seed=1000 * pi + 7, **kw)
+        got = _run(eng, sb)["llr"]
+        ref = O.receiver_forward(net, arch, sb.y, grid.pilots, grid.pilot_mask, sb.active_tx)["llr"]
+        n = ref.shape[-1]
+        b = sb.bits[..., :n].astype(np.float32)
+
+        def stats(llr):
+            ber = float(np.mean((llr > 0) != (b > 0.5)))
+            bmi = float(np.mean(1.0 - np.logaddexp(0.0, -(2.0 * b - 1.0) * llr) / np.log(2.0)))
+            return ber, bmi
+        (ber_g, bmi_g), (ber_o, bmi_o) = stats(got), stats(ref)
+        assert abs(ber_g - ber_o) <= 2e-4 + 0.02 * ber_o, (label, ebno, ber_g, ber_o)
+        assert abs(bmi_g - bmi_o) <= 2e-3, (label, ebno, bmi_g, bmi_o)
+        bers.append(ber_g)
+        bmis.append(bmi_g)
+    if kind == "shipped":
+        assert bers[1] < bers[0] and bmis[1] > bmis[0]
     eng.close()
