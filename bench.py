@@ -8,13 +8,16 @@
 One *step* = one pass of the hot path over one batch of ``batch_size_eval`` = 30 synthetic slots of
 BASELINE.json ``configs[1]`` (nrx_large, 132 PRB, 2 UEs, 4 rx antennas, 16-QAM) per GPU.  Prints ONE
 JSON line: ``value`` = whole-job slots/s with inputs resident in HBM, ``e2e`` = the same through
-the host-buffer C-ABI call (H2D + D2H inside the timed region), plus ``roofline`` (dominant
-kernel, CUDA events around every launch), ``cpu_baseline`` (the oracle port on the host cores),
-``latency_us`` (batch-1 p50 / p99 for nrx_rt and nrx_large) and ``clocks``.
+the host-buffer C-ABI call on page-locked host buffers (every step's H2D and D2H copies inside the
+timed region; two asynchronous calls in flight, the serving pattern), plus ``roofline`` (dominant
+kernel, CUDA events around every launch, fraction of the burst AND of the sustained measured tensor
+peak), ``sustained`` (the same loop run back to back for >= 5 s), ``cpu_baseline`` (the oracle port on
+the host cores), ``latency_us`` (batch-1 p50 / p99 for nrx_rt and nrx_large: device-resident and through
+host buffers) and ``clocks``.
 
-``--impl reference`` times the reference's own CPU path.  TensorFlow and Sionna are not
-installable here and the fork's torch port does not run, so that arm is the
-oracle restatement (``oracle/nrx_oracle.py``, PyTorch-CPU fp32, all host threads).
+``--impl reference`` times the reference's own CPU path on the same workload: whole 30-slot steps on all
+host threads.  TensorFlow and Sionna are not installable here and the fork's torch port does not run
+(SURVEY.md §0), so that arm is the oracle restatement (``oracle/nrx_oracle.py``, PyTorch-CPU fp32).
 """
 from __future__ import annotations
 
@@ -41,6 +44,25 @@ METRIC = "nrx_slots_per_s"
 UNIT = "slots/s"
 
 
+def workload_desc(cfg):
+    """The SAME string in both arms (the driver compares them)."""
+    return (f"{cfg.label}.cfg: {cfg.n_size_bwp} PRB x 14 symbols, "
+            f"{cfg.max_num_tx} UEs, {cfg.num_rx_antennas} rx antennas, 16-QAM, {cfg.num_nrx_iter} CGNN iterations, "
+            f"batch {cfg.batch_size_eval} slots per GPU per step")
+
+
+def source_hash():
+    """Hash of the kernel sources: keys the committed ncu traffic figures to the code they were measured on
+    (the GPU box has no .git)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "neural_rx_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def _weights(cfg):
     p = os.path.join(ROOT, "weights", f"{cfg.label}_weights")      # staged copy of the reference's weight file
     if os.path.exists(p):
@@ -49,12 +71,13 @@ def _weights(cfg):
 
 
 def _measured_peaks():
+    """(burst TFLOP/s, sustained TFLOP/s, HBM GB/s, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("bf16_tflops_sustained", 1388.1), d.get("hbm_gbs", 6523.3), "MEASURED_PEAKS.json (sustained bf16)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return d.get("bf16_tflops", 1659.2), d.get("bf16_tflops_sustained", 1388.1), d.get("hbm_gbs", 6523.3), "MEASURED_PEAKS.json"
+    return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -97,8 +120,10 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def oracle_slots_per_s(cfg, weights, grid, sb, n_slots: int, threads: int):
-    """Time the CPU restatement of the path (oracle) on ``n_slots`` slots; returns (slots/s, seconds)."""
+def oracle_forward_timer(cfg, weights, grid, threads: int):
+    """Returns run(y, active, chunk) -> seconds for one pass of the CPU restatement of the path (oracle) over the
+    slots of ``y`` in sub-batches of ``chunk`` slots (1 = slot by slot, as the reference's evaluation loop would call
+    it with batch 1; larger = batched tensors)."""
     import torch
     from oracle import nrx_oracle as O
     from tests.common import oracle_arch
@@ -106,40 +131,50 @@ def oracle_slots_per_s(cfg, weights, grid, sb, n_slots: int, threads: int):
     arch = oracle_arch(cfg)
     net = O.bind_weights(arch, weights.to_list())
     tables = dict(nn=grid.nn_index, pe=grid.pos_enc)
-    O.receiver_forward(net, arch, sb.y[:1], grid.pilots, grid.pilot_mask, sb.active_tx[:1], tables=tables)  # warm-up
-    t0 = time.perf_counter()
-    for i in range(n_slots):
-        j = i % sb.y.shape[0]
-        O.receiver_forward(net, arch, sb.y[j:j + 1], grid.pilots, grid.pilot_mask, sb.active_tx[j:j + 1], tables=tables)
-    dt = time.perf_counter() - t0
-    return n_slots / dt, dt
+
+    def run(y, active, chunk):
+        t0 = time.perf_counter()
+        for j in range(0, y.shape[0], chunk):
+            O.receiver_forward(net, arch, y[j:j + chunk], grid.pilots, grid.pilot_mask, active[j:j + chunk], tables=tables)
+        return time.perf_counter() - t0
+    return run
+
+
+def pick_cpu_mode(run, sb):
+    """Slot-by-slot or batched (5 slots per call: the activations of more slots no longer fit the host caches)?
+    Timed on 5 slots each; the faster one is used."""
+    run(sb.y[:1], sb.active_tx[:1], 1)                                          # warm-up (thread pool, allocator)
+    t1 = run(sb.y[:5], sb.active_tx[:5], 1)
+    t5 = run(sb.y[:5], sb.active_tx[:5], 5)
+    return (5, t1, t5) if t5 < t1 else (1, t1, t5)
 
 
 def run_reference(args, rank):
-    """Reference arm: CPU implementation of the path on the host cores (rank 0 only)."""
+    """Reference arm: CPU implementation of the path on the host cores (rank 0 only): every step is one pass over
+    the whole 30-slot batch of the workload."""
     if rank != 0:
         return
     cfg = get_config(WORKLOAD)
     weights, wsrc = _weights(cfg)
     grid = build_grid(cfg)
-    sb = make_slots(cfg, grid, batch=2, ebno_db=4.0, seed=2024)
+    B = cfg.batch_size_eval
+    sb = make_slots(cfg, grid, batch=B, ebno_db=np.linspace(-2, 6, B), seed=1000)
     cores = os.cpu_count() or 1
-    per_step = 2                       # bounded sample: 2 of the 30 slots of a step
-    for _ in range(args.warmup):
-        oracle_slots_per_s(cfg, weights, grid, sb, 1, cores)
-    t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
-        _, dt = oracle_slots_per_s(cfg, weights, grid, sb, per_step, cores)
-        t_total += dt
-        n_total += per_step
-    v = n_total / t_total
-    sample = f"{per_step} slots per step x {args.steps} steps of the {cfg.batch_size_eval}-slot batch ({wsrc})"
+    run = oracle_forward_timer(cfg, weights, grid, cores)
+    chunk, t1, t5 = pick_cpu_mode(run, sb)
+    for _ in range(max(args.warmup - 1, 0)):
+        run(sb.y[:chunk], sb.active_tx[:chunk], chunk)
+    t_steps = [run(sb.y, sb.active_tx, chunk) for _ in range(args.steps)]
+    t_total = float(sum(t_steps))
+    v = B * args.steps / t_total
+    sample = (f"{args.steps} whole steps of {B} slots, {'slot by slot' if chunk == 1 else f'{chunk} slots per call'} "
+              f"(5-slot probe: {t1:.2f} s slot by slot, {t5:.2f} s batched), {wsrc}")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * cfg.batch_size_eval / v, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "nrx_large.cfg: 132 PRB x 14 symbols, 2 UEs, 4 rx antennas, 16-QAM, batch 30",
-                   "note": "TensorFlow/Sionna reference cannot run offline; CPU restatement (oracle port) timed"},
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": f"synthetic ({wsrc})",
+        "config": {"workload": workload_desc(cfg),
+                   "note": "TensorFlow/Sionna reference cannot run offline; its CPU restatement (oracle port) is timed"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -172,7 +207,29 @@ def latency_percentiles(eng, y1, act1, n: int = 200):
     e50, e99 = measure(lambda: eng.forward(y1, act1, want=want, out=outs))
     graph, _ = eng.capture(y1, act1, want=want)
     g50, g99 = measure(graph.replay)
-    return {"p50": g50, "p99": g99, "eager_p50": e50, "eager_p99": e99, "n": n, "mode": "cuda graph replay"}
+    # the same slot through HOST buffers (page-locked): H2D of y, kernels, D2H of the LLRs and the refined channel
+    # estimate, wall clock around the blocking C-ABI call — comparable with the reference's published end-to-end
+    # latency (notebooks/real_time_nrx.ipynb:580-584: 1.409 ms incl. 0.050 H2D / 0.085 D2H, RTX 3090, TensorRT)
+    from neural_rx_b200.engine import pinned_empty
+    y_h = pinned_empty(tuple(y1.shape), np.complex64)
+    y_h[...] = y1.cpu().numpy()
+    a_h = pinned_empty(tuple(act1.shape), np.float32)
+    a_h[...] = act1.cpu().numpy()
+    g_ = eng.grid
+    out_h = {"llr": pinned_empty((1, g_.num_tx, g_.num_data_res * eng.cfg.num_bits_per_symbol[0])),
+             "h_hat_refined": pinned_empty((1, g_.num_tx, g_.num_subcarriers, g_.num_ofdm_symbols, 2 * eng.cfg.num_rx_antennas))}
+    for _ in range(10):
+        eng.forward_host(y_h, a_h, want=want, out=out_h)
+    th = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        eng.forward_host(y_h, a_h, want=want, out=out_h)
+        th.append((time.perf_counter() - t0) * 1e6)
+    th = np.sort(np.asarray(th))
+    return {"p50": g50, "p99": g99, "eager_p50": e50, "eager_p99": e99, "host_p50": float(th[len(th) // 2]),
+            "host_p99": float(th[min(len(th) - 1, int(0.99 * len(th)))]), "n": n,
+            "mode": "p50/p99: cuda graph replay, device-resident; eager_*: plain launches; host_*: blocking host-buffer call "
+                    "(pinned), H2D + kernels + D2H, wall clock"}
 
 
 def main():
@@ -204,6 +261,14 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the receiver has no CPU path)")
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one disjoint block of host cores per rank: the ranks' copy / launch threads do not migrate over each other
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(len(cpus) // world, 1)
+            os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per] or cpus))
+        except OSError:
+            pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -261,7 +326,13 @@ def main():
         eng.forward(ys[i % NBUF], act, want=want, out=outs)
     prof = eng.get_profile()
     eng.set_profiling(False)
-    peak_tf, peak_hbm, peak_src = _measured_peaks()
+    peak_burst, peak_sust, peak_hbm, peak_src = _measured_peaks()
+    clocks_mid = clk.summary()
+    # which peak applies: the burst figure while the SM clock sits at its maximum with no power capping (a short
+    # run), the sustained one once the part is power-capped
+    uncapped = (clocks_mid.get("sm_mhz") or 0) >= 0.95 * (clocks_mid.get("sm_max_mhz") or 1e9) and \
+        "sw_power_cap" not in clocks_mid.get("reasons", [])
+    peak_tf = peak_burst if uncapped else peak_sust
     P_step = B * grid.num_tx * grid.num_subcarriers * grid.num_ofdm_symbols     # user-REs per step
     dom = max(prof, key=lambda k: prof[k]["ms"])
     # algorithmic FLOPs of the dominant kernel per launch = 2 * MACs/pixel of that layer * pixels per launch
@@ -284,22 +355,49 @@ def main():
         flops_per_launch = 2.0 * mac_layer[dom] * pixels_per_launch
         dur_s = prof[dom]["ms"] * 1e-3 / n_l
         achieved = flops_per_launch / dur_s / 1e12
-        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same workload)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        ncu_name = {"stack_update": "nrx_stack_kernel<1, 0>", "stack_init": "nrx_stack_kernel<0, 0>",
+        # DRAM bytes per launch of that kernel from this round's committed `ncu --set full` capture — only if it was
+        # taken on the kernel sources that are running now (tools/ncu_summary.py stores their hash)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        ncu_name = {"stack_update": "nrx_stack_ws_kernel<1>" if args.fused == 5 else "nrx_stack_kernel<1, 0>",
+                    "stack_init": "nrx_stack_ws_kernel<0>" if args.fused == 5 else "nrx_stack_kernel<0, 0>",
                     "agg": "nrx_agg_kernel<2>", "readout": "nrx_readout_kernel"}.get(dom)
-        if os.path.exists(tpath) and ncu_name and passes == 1 and args.fused == 1:
+        if os.path.exists(tpath) and ncu_name and passes == 1:
             with open(tpath) as f:
-                traffic = json.load(f).get(ncu_name, {}).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("source_hash") == source_hash():
+                traffic = tj.get("kernels", {}).get(ncu_name, {}).get("dram_bytes_per_launch")
+                traffic_src = f"profiles/r02_traffic.json (ncu --set full, source hash {tj.get('source_hash')})"
+            else:
+                traffic_src = "omitted: profiles/r02_traffic.json was captured on other kernel sources"
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                "algorithmic_bytes_per_launch": 512.0 * pixels_per_launch if dom == "stack_update" else None,
+                "frac": achieved / peak_tf, "frac_of_burst_peak": achieved / peak_burst,
+                "frac_of_sustained_peak": achieved / peak_sust,
+                "peak_used": "burst" if uncapped else "sustained", "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_unit": "bytes per launch (ncu dram read+write)",
+                # per user-RE: 11/9 x 256 B input window + 128 B residual re-read + 128 B new state
+                "algorithmic_bytes_per_launch": 340.0 * pixels_per_launch if dom == "stack_update" else None,
                 "peak_source": peak_src,
                 "launch_us": dur_s * 1e6, "launches_per_step": launches_per_step,
                 "share_of_kernel_time": prof[dom]["ms"] / max(total_kernel_ms, 1e-9)}
     whole = {"achieved_tflops": eng.flops_per_slot() * value / world / 1e12,
-             "frac_of_peak": eng.flops_per_slot() * value / world / 1e12 / peak_tf}
+             "frac_of_peak": eng.flops_per_slot() * value / world / 1e12 / peak_tf,
+             "frac_of_burst_peak": eng.flops_per_slot() * value / world / 1e12 / peak_burst}
+
+    # ---- steady state: the same loop back to back for >= 5 s (a power-cap effect would show here) -------
+    sust_clk = ClockSampler(local_rank)
+    sust_clk.__enter__()
+    n_sust = max(int(5.5 / max(ms / args.steps * 1e-3, 1e-6)), args.steps)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(n_sust):
+        eng.forward(ys[i % NBUF], act, want=want, out=outs)
+    s1.record()
+    barrier()
+    sust_ms = max_over_ranks(s0.elapsed_time(s1))
+    sust_clk.__exit__(None, None, None)
+    sustained = {"seconds": sust_ms * 1e-3, "steps": n_sust, "value": world * B * n_sust / (sust_ms * 1e-3), "unit": UNIT,
+                 "clocks": sust_clk.summary()}
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
     # inputs and outputs live in page-locked host memory (the contract's "pinned host memory"); every
@@ -316,19 +414,36 @@ def main():
                                               2 * cfg.num_rx_antennas))}
     if args.host_chunk:
         eng.set_host_chunk(args.host_chunk)
+    # two result sets and two calls in flight: step i+1 is enqueued before step i is waited for, so its copy-in
+    # overlaps step i's kernels and copy-outs (nrx_forward_host_async / nrx_wait)
+    act_pin = pinned_empty(base.active_tx.shape, np.float32)
+    act_pin[...] = base.active_tx
+    out_pins = [out_pin, {k: pinned_empty(v.shape) for k, v in out_pin.items()}]
     for i in range(3):
-        eng.forward_host(ys_pin[i % NBUF], base.active_tx, want=want, out=out_pin)
+        eng.wait(eng.forward_host_async(ys_pin[i % NBUF], act_pin, out_pins[i % 2]))
     barrier()
     t0 = time.perf_counter()
+    prev = None
     for i in range(args.steps):
-        res = eng.forward_host(ys_pin[i % NBUF], base.active_tx, want=want, out=out_pin)
+        t = eng.forward_host_async(ys_pin[i % NBUF], act_pin, out_pins[i % 2])
+        if prev is not None:
+            eng.wait(prev)
+        prev = t
+    res = eng.wait(prev)
     barrier()
     dt = time.perf_counter() - t0
     dt = max_over_ranks(dt)
-    h2d = ys_pin[0].nbytes + base.active_tx.nbytes
+    h2d = ys_pin[0].nbytes + act_pin.nbytes
     d2h = sum(v.nbytes for v in res.values())
     e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "host_memory": "pinned", "host_chunk_slots": args.host_chunk or min(16, (B + 2) // 3)}
+           "d2h_bytes_per_step": int(d2h), "host_memory": "pinned", "calls_in_flight": 2,
+           "host_chunk_slots": args.host_chunk or min(16, (B + 2) // 3)}
+    # one blocking call per step (nothing overlaps between steps)
+    t0 = time.perf_counter()
+    for i in range(max(args.steps // 2, 1)):
+        eng.forward_host(ys_pin[i % NBUF], base.active_tx, want=want, out=out_pin)
+    barrier()
+    e2e["blocking_call_value"] = world * B * max(args.steps // 2, 1) / max_over_ranks(time.perf_counter() - t0)
     # same call with ordinary (pageable) NumPy arrays, staged through the engine's pinned buffers
     t0 = time.perf_counter()
     for i in range(max(args.steps // 2, 1)):
@@ -375,20 +490,22 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = 96                      # ~10 s of CPU work on the box's host cores
-            v_cpu, dt_cpu = oracle_slots_per_s(cfg, weights, grid, base, n_cpu, cores)
-            cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu} slots of the same batch through oracle/nrx_oracle.py (PyTorch-CPU fp32), {dt_cpu:.1f} s"}
+            run = oracle_forward_timer(cfg, weights, grid, cores)
+            chunk, _, _ = pick_cpu_mode(run, base)
+            n_cpu = 3 * B                   # ~10 s of CPU work on the box's host cores
+            dt_cpu = sum(run(base.y, base.active_tx, chunk) for _ in range(3))
+            cpu = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"3 whole steps ({n_cpu} slots) of the same batch through oracle/nrx_oracle.py (PyTorch-CPU fp32, "
+                             f"{'slot by slot' if chunk == 1 else f'{chunk} slots per call'}), {dt_cpu:.1f} s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": f"synthetic ({wsrc})",
-            "config": {"workload": "nrx_large.cfg: 132 PRB x 14 symbols, 2 UEs, 4 rx antennas, 16-QAM, "
-                                   f"{cfg.num_nrx_iter} CGNN iterations, batch {B} slots per GPU per step",
-                       "slots_per_pass": args.slots_per_pass or B,
+            "config": {"workload": workload_desc(cfg),
+                       "slots_per_pass": args.slots_per_pass or B, "plan": args.fused,
                        "l2": f"inputs rotate over {NBUF} distinct batches ({NBUF * ys_host[0].nbytes / 1e6:.0f} MB > 126 MB L2)",
                        "parallelism": f"slot-sharded x{world}, no data-path collective"},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "whole_path": whole,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "whole_path": whole, "sustained": sustained,
             "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
             "cpu_baseline": cpu, "clocks": clk.summary(), "slots_processed": slots_done,
         }

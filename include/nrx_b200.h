@@ -161,6 +161,19 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
                      int32_t out_bits, float* llr, float* llr_grid, float* h_hat_refined,
                      float* h_hat_ls);
 
+/* The same call, asynchronous: it only ENQUEUES the copies and kernels and returns a ticket; nrx_wait(ticket)
+ * blocks until all outputs of that call are in the caller's buffers.  All buffers (inputs and outputs) must be
+ * page-locked host memory (cudaHostAlloc / cudaHostRegister / pinned torch tensors) — NRX_ERR_INVALID otherwise —
+ * and belong to the engine until nrx_wait returns.  Up to 4 calls may be in flight: the chunk pipeline runs on
+ * across calls, so the copy-in of call n+1 overlaps the kernels and copy-outs of call n (a serving loop keeps two
+ * calls in flight and never exposes a transfer).  Calls complete in order.  Replaces the same reference call as
+ * nrx_forward_host; the reference itself is synchronous (utils/neural_rx.py:1544-1603). */
+int nrx_forward_host_async(nrx_engine* e, int32_t batch, const void* y, const float* active_tx,
+                           const int32_t* io_index, const int32_t* head_index, int32_t llr_head,
+                           int32_t out_bits, float* llr, float* llr_grid, float* h_hat_refined,
+                           float* h_hat_ls, int64_t* ticket);
+int nrx_wait(nrx_engine* e, int64_t ticket);
+
 /* Slots per pipeline chunk of nrx_forward_host (0 = default: a third of the batch, at most 16). */
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots);
 

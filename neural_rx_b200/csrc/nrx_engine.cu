@@ -131,6 +131,13 @@ struct nrx_engine {
     int host_chunk = 0;                             // slots per pipeline chunk (0 = default)
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[kRing] = {}, ev_comp[kRing] = {}, ev_d2h[kRing] = {};
+    // asynchronous host calls (nrx_forward_host_async): the chunk ring runs on across calls, every call has a ticket
+    static constexpr int kCalls = 4;                // calls that may be in flight
+    uint64_t chunk_seq = 0;                         // chunks enqueued so far (ring slot = chunk_seq % kRing)
+    uint64_t call_seq = 0;                          // tickets handed out so far
+    cudaEvent_t ev_call[kCalls] = {};               // recorded after the last device-to-host copy of a call
+    size_t arena_chunk_slots = 0;                   // slots per chunk the ring buffers are sized for
+    int arena_outs = 0;                             // output mask the ring buffers are sized for
     void* h_pin = nullptr;
     size_t h_pin_bytes = 0;
     void* d_io = nullptr;
@@ -140,6 +147,8 @@ struct nrx_engine {
 };
 
 namespace {
+
+int host_streams(nrx_engine* e);
 
 struct Workspace {
     size_t partial, z0, h1, h2, abuf, abuf2, sbuf, sbuf2, total;
@@ -465,6 +474,8 @@ int nrx_destroy(nrx_engine* e) {
             if (e->ev_comp[r]) cudaEventDestroy(e->ev_comp[r]);
             if (e->ev_d2h[r]) cudaEventDestroy(e->ev_d2h[r]);
         }
+        for (int c = 0; c < nrx_engine::kCalls; ++c)
+            if (e->ev_call[c]) cudaEventDestroy(e->ev_call[c]);
     }
     for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
@@ -1176,6 +1187,124 @@ int nrx_debug_tm_cycles(unsigned long long* out32) {
 #endif
 #endif
 
+// Asynchronous host-buffer call.  All buffers must be page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
+// tensors): they are DMA'd in place.  The call only enqueues: chunk i's H2D copy, kernels and D2H copies go to three
+// streams and are ordered by events; the ring of kRing chunk buffers runs on across calls, so the first copy-in of
+// call n+1 overlaps the kernels and copy-outs of call n.  Up to kCalls calls may be in flight; the buffers of a
+// call belong to the engine until nrx_wait(ticket) has returned.
+int nrx_forward_host_async(nrx_engine* e, int32_t batch, const void* y, const float* active_tx, const int32_t* io_index,
+                           const int32_t* head_index, int32_t llr_head, int32_t out_bits, float* llr, float* llr_grid,
+                           float* h_hat_refined, float* h_hat_ls, int64_t* ticket) {
+    if (!e || !y || !active_tx || !ticket) return fail(NRX_ERR_INVALID, "nrx_forward_host_async: null argument");
+    if (batch < 1) return fail(NRX_ERR_INVALID, "batch must be >= 1");
+    if (out_bits < 1 || out_bits > 16) return fail(NRX_ERR_INVALID, "out_bits out of range");
+    const nrx_model_desc& d = e->d;
+    NRX_CUDA(cudaSetDevice(e->device));
+    constexpr int R = nrx_engine::kRing, NC = nrx_engine::kCalls;
+    if (int rc = host_streams(e)) return rc;
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    float* outs[4] = {llr, llr_grid, h_hat_refined, h_hat_ls};
+    bool ok = pinned(y) && pinned(active_tx) && (!io_index || pinned(io_index)) && (!head_index || pinned(head_index));
+    for (int k = 0; k < 4; ++k) ok = ok && (!outs[k] || pinned(outs[k]));
+    if (!ok) return fail(NRX_ERR_INVALID, "nrx_forward_host_async needs page-locked buffers (use nrx_forward_host for pageable memory)");
+
+    const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
+    int c = e->host_chunk > 0 ? e->host_chunk : (batch + 2) / 3;
+    if (e->host_chunk <= 0 && c > 16) c = 16;
+    if (c > batch) c = batch;
+    const size_t y_slot = size_t(d.num_rx_ant) * per_slot * 8;
+    // ring buffers are sized for the widest output set (16 values per RE) so that calls with different heads share them
+    const size_t out_cap[4] = {U * d.num_data_res * 16 * 4, U * per_slot * 16 * 4, U * per_slot * N2 * 4, U * per_slot * N2 * 4};
+    const size_t out_slot[4] = {U * d.num_data_res * out_bits * 4, U * per_slot * out_bits * 4, U * per_slot * N2 * 4,
+                                U * per_slot * N2 * 4};
+    int mask = 0;
+    for (int k = 0; k < 4; ++k) mask |= outs[k] ? 1 << k : 0;
+    const size_t small_cap = align_up(size_t(4096) * U * 4, 256);          // per call: active_tx | io_index | head_index
+    if (size_t(batch) * U * 4 > small_cap) return fail(NRX_ERR_INVALID, "batch too large for the asynchronous call (<= 4096 slots)");
+    // device arena: [NC x 3 small arrays][R x (y chunk | 4 output chunks)]
+    size_t off = 0;
+    auto piece = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_small[NC][3];
+    for (int q = 0; q < NC; ++q)
+        for (int k = 0; k < 3; ++k) o_small[q][k] = piece(small_cap);
+    const size_t C = size_t(c) > e->arena_chunk_slots ? size_t(c) : e->arena_chunk_slots;
+    const int amask = mask | e->arena_outs;
+    size_t o_y[R], o_out[R][4];
+    for (int r = 0; r < R; ++r) {
+        o_y[r] = piece(C * y_slot);
+        for (int k = 0; k < 4; ++k) o_out[r][k] = piece((amask >> k) & 1 ? C * out_cap[k] : 0);
+    }
+    if (off > e->d_io_bytes || C != e->arena_chunk_slots || amask != e->arena_outs) {     // (re)size: nothing may be in flight
+        NRX_CUDA(cudaDeviceSynchronize());
+        if (off > e->d_io_bytes) {
+            cudaFree(e->d_io);
+            e->d_io = nullptr;
+            e->d_io_bytes = 0;
+            NRX_CUDA(cudaMalloc(&e->d_io, off));
+            e->d_io_bytes = off;
+        }
+        e->arena_chunk_slots = C;
+        e->arena_outs = amask;
+    }
+    const Workspace w = layout(e, int(C));
+    if (w.total > e->d_ws_bytes) {
+        NRX_CUDA(cudaDeviceSynchronize());
+        cudaFree(e->d_ws);
+        e->d_ws = nullptr;
+        e->d_ws_bytes = 0;
+        NRX_CUDA(cudaMalloc(&e->d_ws, w.total));
+        e->d_ws_bytes = w.total;
+    }
+    const int q = int(e->call_seq % NC);
+    if (e->call_seq >= uint64_t(NC)) NRX_CUDA(cudaEventSynchronize(e->ev_call[q]));      // the call that used this ticket slot
+    uint8_t* dp = static_cast<uint8_t*>(e->d_io);
+    const size_t BU = size_t(batch) * U;
+    NRX_CUDA(cudaMemcpyAsync(dp + o_small[q][0], active_tx, BU * 4, cudaMemcpyHostToDevice, e->s_h2d));
+    if (io_index) NRX_CUDA(cudaMemcpyAsync(dp + o_small[q][1], io_index, BU * 4, cudaMemcpyHostToDevice, e->s_h2d));
+    if (head_index) NRX_CUDA(cudaMemcpyAsync(dp + o_small[q][2], head_index, BU * 4, cudaMemcpyHostToDevice, e->s_h2d));
+    for (int b0 = 0; b0 < batch; b0 += c) {
+        const int n = batch - b0 < c ? batch - b0 : c;
+        const int r = int(e->chunk_seq % R);
+        if (e->chunk_seq >= uint64_t(R)) NRX_CUDA(cudaStreamWaitEvent(e->s_h2d, e->ev_d2h[r], 0));   // slot's previous chunk is out
+        NRX_CUDA(cudaMemcpyAsync(dp + o_y[r], static_cast<const uint8_t*>(y) + size_t(b0) * y_slot, size_t(n) * y_slot,
+                                 cudaMemcpyHostToDevice, e->s_h2d));
+        NRX_CUDA(cudaEventRecord(e->ev_h2d[r], e->s_h2d));
+        NRX_CUDA(cudaStreamWaitEvent(e->stream, e->ev_h2d[r], 0));
+        const int rc = nrx_forward(e, e->stream, n, dp + o_y[r], reinterpret_cast<const float*>(dp + o_small[q][0]) + size_t(b0) * U,
+                                   io_index ? reinterpret_cast<const int32_t*>(dp + o_small[q][1]) + size_t(b0) * U : nullptr,
+                                   head_index ? reinterpret_cast<const int32_t*>(dp + o_small[q][2]) + size_t(b0) * U : nullptr,
+                                   llr_head, out_bits, outs[0] ? reinterpret_cast<float*>(dp + o_out[r][0]) : nullptr,
+                                   outs[1] ? reinterpret_cast<float*>(dp + o_out[r][1]) : nullptr,
+                                   outs[2] ? reinterpret_cast<float*>(dp + o_out[r][2]) : nullptr,
+                                   outs[3] ? reinterpret_cast<float*>(dp + o_out[r][3]) : nullptr, e->d_ws, e->d_ws_bytes);
+        if (rc) return rc;
+        NRX_CUDA(cudaEventRecord(e->ev_comp[r], e->stream));
+        NRX_CUDA(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[r], 0));
+        for (int k = 0; k < 4; ++k)
+            if (outs[k])
+                NRX_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(outs[k]) + size_t(b0) * out_slot[k], dp + o_out[r][k],
+                                         size_t(n) * out_slot[k], cudaMemcpyDeviceToHost, e->s_d2h));
+        NRX_CUDA(cudaEventRecord(e->ev_d2h[r], e->s_d2h));
+        ++e->chunk_seq;
+    }
+    NRX_CUDA(cudaEventRecord(e->ev_call[q], e->s_d2h));
+    *ticket = int64_t(e->call_seq++);
+    return NRX_OK;
+}
+
+// Blocks until the call that returned `ticket` has delivered all its outputs.
+int nrx_wait(nrx_engine* e, int64_t ticket) {
+    if (!e || ticket < 0 || uint64_t(ticket) >= e->call_seq) return fail(NRX_ERR_INVALID, "nrx_wait: unknown ticket");
+    if (e->call_seq - uint64_t(ticket) > uint64_t(nrx_engine::kCalls)) return NRX_OK;      // its slot has been recycled: long done
+    NRX_CUDA(cudaSetDevice(e->device));
+    NRX_CUDA(cudaEventSynchronize(e->ev_call[ticket % nrx_engine::kCalls]));
+    return NRX_OK;
+}
+
 // ---- test hooks: ONE kernel of the path on caller-provided device tensors ----------------------------------------
 // (tests/test_gpu_kernels.py drives them with random tensors at edge-case widths; not used by the product path)
 int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t batch, const void* s_f16, const float* active_tx,
@@ -1258,6 +1387,26 @@ int nrx_set_host_chunk(nrx_engine* e, int32_t slots) {
     return NRX_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int host_streams(nrx_engine* e) {                      // three streams + ring events of the host-buffer calls
+    if (e->stream) return NRX_OK;
+    NRX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    NRX_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    NRX_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    for (int r = 0; r < nrx_engine::kRing; ++r) {
+        NRX_CUDA(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
+        NRX_CUDA(cudaEventCreateWithFlags(&e->ev_comp[r], cudaEventDisableTiming));
+        NRX_CUDA(cudaEventCreateWithFlags(&e->ev_d2h[r], cudaEventDisableTiming));
+    }
+    for (int c = 0; c < nrx_engine::kCalls; ++c) NRX_CUDA(cudaEventCreateWithFlags(&e->ev_call[c], cudaEventDisableTiming));
+    return NRX_OK;
+}
+}  // namespace
+
+extern "C" {
+
 // Host-buffer call: the batch is cut into chunks of `host_chunk` slots that flow through a
 // three-stage pipeline on three streams — H2D of chunk i+1, kernels of chunk i and D2H of chunk
 // i-1 overlap.  Pinned (page-locked / registered) user buffers are DMA'd directly; pageable ones
@@ -1271,15 +1420,13 @@ int nrx_forward_host(nrx_engine* e, int32_t batch, const void* y, const float* a
     const nrx_model_desc& d = e->d;
     NRX_CUDA(cudaSetDevice(e->device));
     constexpr int R = nrx_engine::kRing;
-    if (!e->stream) {
-        NRX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        NRX_CUDA(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
-        NRX_CUDA(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
-        for (int r = 0; r < R; ++r) {
-            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
-            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_comp[r], cudaEventDisableTiming));
-            NRX_CUDA(cudaEventCreateWithFlags(&e->ev_d2h[r], cudaEventDisableTiming));
-        }
+    if (int rc = host_streams(e)) return rc;
+    // the synchronous call uses the ring from slot 0 with its own layout: drain whatever asynchronous calls left behind
+    if (e->arena_chunk_slots) {
+        NRX_CUDA(cudaDeviceSynchronize());
+        e->chunk_seq = 0;
+        e->arena_chunk_slots = 0;
+        e->arena_outs = 0;
     }
     const size_t U = d.max_num_tx, per_slot = size_t(d.num_subcarriers) * kT, N2 = 2 * d.num_rx_ant;
     // Chunk schedule: uniform chunks, by default a third of the batch and at most 16 slots (three chunks in flight).

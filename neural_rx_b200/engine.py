@@ -23,7 +23,7 @@ NRX_MAX_DMRS = 4
 #: every symbol declared in include/nrx_b200.h
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
-    "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
+    "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_forward_host_async", "nrx_wait", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
     "nrx_plan_stack_chunks",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
     "nrx_debug_aggregate", "nrx_debug_stack", "nrx_debug_readout",
@@ -87,6 +87,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
                                 ctypes.c_void_p, ctypes.c_size_t]
     lib.nrx_forward_host.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p, i32p, i32p,
                                      ctypes.c_int32, ctypes.c_int32, f32p, f32p, f32p, f32p]
+    lib.nrx_forward_host_async.argtypes = lib.nrx_forward_host.argtypes + [ctypes.POINTER(ctypes.c_int64)]
+    lib.nrx_wait.argtypes = [ctypes.c_void_p, ctypes.c_int64]
     lib.nrx_set_aerial_dmrs.argtypes = [ctypes.c_void_p, i32p, ctypes.c_int32, i32p, ctypes.c_int32]
     lib.nrx_forward_aerial.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, f32p, f32p, f32p, f32p, f32p,
                                        f32p, f32p, ctypes.c_void_p, ctypes.c_size_t]
@@ -442,6 +444,58 @@ class NrxEngine:
             None if hd is None else hd.ctypes.data, int(llr_head), bits, ptr("llr"), ptr("llr_grid"),
             ptr("h_hat_refined"), ptr("h_hat")))
         return res
+
+
+def _host_shapes(eng, B, bits):
+    g, N, U = eng.grid, eng.cfg.num_rx_antennas, eng.grid.num_tx
+    return {"llr": (B, U, g.num_data_res * bits), "llr_grid": (B, U, g.num_subcarriers, g.num_ofdm_symbols, bits),
+            "h_hat_refined": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N),
+            "h_hat": (B, U, g.num_subcarriers, g.num_ofdm_symbols, 2 * N)}
+
+
+def forward_host_async(self, y: np.ndarray, active_tx: np.ndarray, out: Dict[str, np.ndarray], io_index=None,
+                       head_index=None, llr_head: int = 0, out_bits: Optional[int] = None) -> int:
+    """Asynchronous host-buffer call (``nrx_forward_host_async``): every array — ``y`` complex64, ``active_tx``
+    float32, the optional int32 index arrays and the float32 result arrays in ``out`` (keys among llr, llr_grid,
+    h_hat_refined, h_hat) — must be page-locked (:func:`pinned_empty`) and C-contiguous with the exact dtype; nothing
+    is copied or converted on the host.  Returns a ticket; the arrays belong to the engine until ``wait(ticket)``."""
+    g, N = self.grid, self.cfg.num_rx_antennas
+    B, U = y.shape[0], g.num_tx
+    if y.dtype != np.complex64 or not y.flags.c_contiguous or y.shape != (B, 1, N, g.num_ofdm_symbols, g.num_subcarriers):
+        raise ValueError(f"y must be C-contiguous complex64 [B,1,{N},{g.num_ofdm_symbols},{g.num_subcarriers}]")
+    if active_tx.dtype != np.float32 or not active_tx.flags.c_contiguous or active_tx.shape != (B, U):
+        raise ValueError(f"active_tx must be C-contiguous float32 [B,{U}]")
+    for name, a in (("io_index", io_index), ("head_index", head_index)):
+        if a is not None and (a.dtype != np.int32 or not a.flags.c_contiguous or a.shape != (B, U)):
+            raise ValueError(f"{name} must be C-contiguous int32 [B,{U}]")
+    bits = self._out_bits(llr_head, head_index, out_bits)
+    shapes = _host_shapes(self, B, bits)
+    for k, a in out.items():
+        if k not in shapes or a.shape != shapes[k] or a.dtype != np.float32 or not a.flags.c_contiguous:
+            raise ValueError(f"out[{k!r}] must be a C-contiguous float32 array of shape {shapes.get(k)}")
+    ptr = lambda k: out[k].ctypes.data if k in out else None
+    ticket = ctypes.c_int64()
+    self._check(self._lib.nrx_forward_host_async(
+        self._h, B, y.ctypes.data, active_tx.ctypes.data, None if io_index is None else io_index.ctypes.data,
+        None if head_index is None else head_index.ctypes.data, int(llr_head), bits, ptr("llr"), ptr("llr_grid"),
+        ptr("h_hat_refined"), ptr("h_hat"), ctypes.byref(ticket)))
+    if not hasattr(self, "_inflight"):
+        self._inflight = {}
+    self._inflight[ticket.value] = (y, active_tx, io_index, head_index, out)      # keep the buffers alive
+    return ticket.value
+
+
+def wait(self, ticket: int) -> Dict[str, np.ndarray]:
+    """Block until the asynchronous call ``ticket`` has delivered its outputs; returns its ``out`` dict."""
+    self._check(self._lib.nrx_wait(self._h, int(ticket)))
+    held = getattr(self, "_inflight", {})
+    for t in [t for t in held if t < ticket]:
+        held.pop(t)                                                             # calls complete in order
+    return held.pop(ticket, (None,) * 5)[4]
+
+
+NrxEngine.forward_host_async = forward_host_async
+NrxEngine.wait = wait
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:

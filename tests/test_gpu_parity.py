@@ -343,6 +343,46 @@ def test_host_call_passes_and_determinism():
     eng.close()
 
 
+def test_async_host_calls_in_flight():
+    """nrx_forward_host_async + nrx_wait: several calls in flight on page-locked buffers (the chunk ring runs on
+    across calls) give the same bits as the synchronous call, in order, also with per-user index arrays and after
+    a synchronous call in between; pageable buffers are refused."""
+    from neural_rx_b200.engine import NrxError, pinned_empty
+    cfg = get_config("nrx_rt_var_mcs")
+    weights, _ = get_weights(cfg)
+    grid = build_grid(cfg, n_size_bwp=9)
+    eng = _engine(cfg, weights, grid)
+    eng.set_host_chunk(2)
+    calls = []
+    for i, B in enumerate((5, 3, 7, 4, 6, 2)):                 # six calls through four ticket slots and three ring slots
+        sb = make_slots(cfg, grid, batch=B, ebno_db=6.0 + i, seed=500 + i, mcs_per_ue=[0, 1])
+        y = pinned_empty(sb.y.shape, np.complex64); y[...] = sb.y
+        act = pinned_empty(sb.active_tx.shape, np.float32); act[...] = sb.active_tx
+        io = pinned_empty((B, 2), np.int32); io[...] = [0, 1]
+        out = {"llr": pinned_empty((B, 2, grid.num_data_res * 4)), "h_hat_refined": pinned_empty((B, 2, grid.num_subcarriers, 14, 8))}
+        ref = eng.forward_host(sb.y, sb.active_tx, io_index=io, llr_head=1, want=("llr", "h_hat_refined"))
+        calls.append((y, act, io, out, ref))
+    tickets = [eng.forward_host_async(y, act, out, io_index=io, llr_head=1) for y, act, io, out, _ in calls[:4]]
+    for t, (_, _, _, out, ref) in zip(tickets, calls[:4]):
+        got = eng.wait(t)
+        assert got is out
+        assert np.array_equal(out["llr"], ref["llr"]) and np.array_equal(out["h_hat_refined"], ref["h_hat_refined"])
+    # two in flight at a time, the serving pattern of bench.py
+    prev = None
+    for y, act, io, out, ref in calls[4:] + calls[:2]:
+        out["llr"][...] = 0
+        t = eng.forward_host_async(y, act, out, io_index=io, llr_head=1)
+        if prev is not None:
+            eng.wait(prev[0])
+            assert np.array_equal(prev[1]["llr"], prev[2]["llr"])
+        prev = (t, out, ref)
+    eng.wait(prev[0])
+    assert np.array_equal(prev[1]["llr"], prev[2]["llr"])
+    with pytest.raises(NrxError, match="page-locked"):
+        eng.forward_host_async(np.ascontiguousarray(calls[0][0]).copy(), calls[0][1], calls[0][3], io_index=calls[0][2], llr_head=1)
+    eng.close()
+
+
 def test_zero_input_and_bad_arguments():
     """divide_no_nan of the normalisation (all-zero slot -> finite outputs); shape errors raise."""
     import torch
