@@ -437,7 +437,7 @@ def main():
     d2h = sum(v.nbytes for v in res.values())
     e2e = {"value": world * B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "host_memory": "pinned", "calls_in_flight": 2,
-           "host_chunk_slots": args.host_chunk or min(16, (B + 2) // 3)}
+           "host_chunk_slots": args.host_chunk or min(32, B)}
     # one blocking call per step (nothing overlaps between steps)
     t0 = time.perf_counter()
     for i in range(max(args.steps // 2, 1)):
@@ -487,6 +487,28 @@ def main():
             extra["nrx_rt_slots_per_s_one_gpu"] = B * n_rt / (r0.elapsed_time(r1) * 1e-3)
             eng_rt.close()
             extra["latency_us"] = lat
+        # inactive-user skipping: the same 30-slot steps with one of the two users switched off
+        # (the reference's 1-UE evaluation points, results/nrx_rt_results key (..., 1, 0)), everything computed as the
+        # reference does vs. only the active planes
+        act_half = act.clone()
+        act_half[:, 1] = 0
+
+        def rate(n=max(args.steps // 2, 5)):
+            for i in range(3):
+                eng.forward(ys[i % NBUF], act_half, want=want, out=outs)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for i in range(n):
+                eng.forward(ys[i % NBUF], act_half, want=want, out=outs)
+            q1.record()
+            torch.cuda.synchronize()
+            return B * n / (q0.elapsed_time(q1) * 1e-3)
+        v_all = rate()
+        eng.set_skip_inactive(True)
+        v_skip = rate()
+        eng.set_skip_inactive(False)
+        extra["one_of_two_ues_active"] = {"all_planes_computed": v_all, "inactive_planes_skipped": v_skip, "unit": UNIT + " (one GPU)"}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -109,6 +109,14 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  * Plans 0, 1 and 5 are bit-identical; plan 2 differs at fp16 round-off. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);
 
+/* Inactive-user skipping (off by default = the reference's behaviour: it computes all users and ignores the
+ * inactive ones, notebooks/nrx_architecture.ipynb:537).  An inactive user's state never reaches an active user
+ * (its messages are masked, utils/neural_rx.py:192-204), so with skipping on the (slot, user) planes of inactive
+ * users are not computed: the LLRs and the refined channel estimate of ACTIVE users are bit-identical, those of
+ * inactive users are zeros instead of the reference's meaningless values.  With one of two users active the
+ * work halves.  Plans 1 and 5 (ignored by the others). */
+int nrx_set_skip_inactive(nrx_engine* e, int32_t enable);
+
 /* Bytes of device scratch nrx_forward needs for `batch` slots. */
 int nrx_workspace_bytes(const nrx_engine* e, int32_t batch, size_t* bytes);
 
@@ -174,7 +182,8 @@ int nrx_forward_host_async(nrx_engine* e, int32_t batch, const void* y, const fl
                            float* h_hat_ls, int64_t* ticket);
 int nrx_wait(nrx_engine* e, int64_t ticket);
 
-/* Slots per pipeline chunk of nrx_forward_host (0 = default: a third of the batch, at most 16). */
+/* Slots per pipeline chunk of the host-buffer calls (0 = default: nrx_forward_host a third of the batch, at most 16;
+ * nrx_forward_host_async whole calls up to 32 slots). */
 int nrx_set_host_chunk(nrx_engine* e, int32_t slots);
 
 /* Number of kernels nrx_forward enqueues for `batch` slots with the current settings. */

@@ -75,6 +75,39 @@ __device__ __forceinline__ float slot_gain(const float* __restrict__ partial, in
 }
 
 // =============================================================================================
+// 1b. inactive-user skipping: ordered list of the (slot, user) planes whose user is active.  An inactive
+//     user's state never reaches an active user (its messages are masked, utils/neural_rx.py:192-193), so
+//     its planes need not be computed at all; the reference computes them and ignores the result
+//     (notebooks/nrx_architecture.ipynb:537).  One block; list[0 .. count) ascending, count in list[-1 + ...]:
+//     out[0] = count, out[1 + i] = i-th active plane.
+// =============================================================================================
+__global__ void __launch_bounds__(1024) nrx_planes_kernel(const float* __restrict__ active_tx, int n_planes, int32_t* __restrict__ out) {
+    __shared__ int warp_cnt[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_planes; i0 += 1024) {
+        const int i = i0 + tid;
+        const bool on = i < n_planes && active_tx[i] != 0.f;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        if (on) out[1 + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[0] = base;
+}
+
+// =============================================================================================
 // 2. pre-processing: LS + FOCC + nearest-pilot broadcast, normalisation, positional encoding
 //    (NeuralPUSCHReceiver.estimate_channel utils/neural_rx.py:1462-1514, copy_pytorch.py:899-911;
 //     CGNNOFDM.forward :832-839; StateInit concat :112-123)
@@ -527,6 +560,8 @@ struct alignas(64) AggParams {
     const uint8_t* wblob;      // [W1 image 64x64 | W2 image 64x64 | b1[64] | b2[64]]
     const float* active_tx;    // [Bp][U] (already offset to the pass)
     int U, rows_per_bu, tiles_per_b, num_tiles;
+    int skip_idle;             // inactive-user skipping: a slot with at most one active user has no messages to
+                               //   compute (every a row of an active user is exactly zero): no GEMMs, zeros stored
 };
 
 constexpr int kAggBlob = 8192 + 8192 + 256 + 256;
@@ -597,6 +632,22 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
 #pragma unroll
         for (int u = 0; u < U; ++u) m[u] = __ldg(p.active_tx + b * U + u);
         mbar_wait(&bar_ld[stage], (it >> 1) & 1);
+        if (p.skip_idle) {
+            float n_on = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) n_on += m[u];
+            if (n_on <= 1.f) {                           // block-uniform: sum over the OTHER active users is empty
+                __syncthreads();                         // (every thread has passed the load barrier of this stage)
+                for (int i = tid; i < U * 128 * 8; i += kThreads) {
+                    const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
+                    if (rr < valid_rows && m[u] != 0.f)
+                        *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
+                            make_uint4(0, 0, 0, 0);
+                }
+                __syncthreads();
+                continue;
+            }
+        }
         tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
@@ -659,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
                 float tot = 0.f;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    sp[u][j] = (sp[u][j] + sB2[col + j]) * m[u];
+                    sp[u][j] = m[u] != 0.f ? (sp[u][j] + sB2[col + j]) * m[u] : 0.f;
                     tot += sp[u][j];
                 }
 #pragma unroll
@@ -709,6 +760,7 @@ struct ReadoutParams {
     int F, U, N2, out_bits, n_data;
     int rows_per_bu, tiles_per_bu, num_tiles, default_head;
     int n_heads;                 // heads in wblob: head_index values are clamped to [0, n_heads)
+    const int32_t* plane_list;   // inactive-user skipping: [0] = number of active planes, [1 + i] = i-th one; or null
     int vec;                     // output pointers are 16-byte aligned: vector stores
 };
 
@@ -750,7 +802,8 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
     constexpr int NV = 128 * 8 / kThreads;
     uint4 pre[NV];
     auto fetch = [&](int tile) {
-        const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
+        const int pl = tile / p.tiles_per_bu, rt = tile - pl * p.tiles_per_bu;
+        const int bu = p.plane_list ? p.plane_list[1 + pl] : pl;
         const int r0 = rt * 128, valid_rows = min(128, p.rows_per_bu - r0);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -761,10 +814,12 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
                 pre[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
         }
     };
-    if (int(blockIdx.x) < p.num_tiles) fetch(blockIdx.x);
+    const int num_tiles = p.plane_list ? p.plane_list[0] * p.tiles_per_bu : p.num_tiles;
+    if (int(blockIdx.x) < num_tiles) fetch(blockIdx.x);
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int bu = tile / p.tiles_per_bu, rt = tile - bu * p.tiles_per_bu;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int pl = tile / p.tiles_per_bu, rt = tile - pl * p.tiles_per_bu;
+        const int bu = p.plane_list ? p.plane_list[1 + pl] : pl;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
         const int head = min(max(p.head_index ? p.head_index[bu] : p.default_head, 0), p.n_heads - 1);
@@ -784,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
             const int rr = i >> 3, cc = i & 7;
             st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
         }
-        if (tile + int(gridDim.x) < p.num_tiles) fetch(tile + gridDim.x);
+        if (tile + int(gridDim.x) < num_tiles) fetch(tile + gridDim.x);
         // demapped position of this thread's row: fetched now, used after the second GEMM (the load used to sit,
         // with its full latency, on the four warps of the output epilogue)
         int d_row = -1;

@@ -53,7 +53,18 @@ struct StackParams {
     int n_chunks, num_items;
     int default_stack;
     int n_stacks;                // stacks in wblob: stack_index values are clamped to [0, n_stacks)
+    const int32_t* plane_list;   // inactive-user skipping: [0] = number of active planes, [1 + i] = i-th one; or null
 };
+
+// work items of a launch and the (slot, user) plane of item `item` (all planes, or only the active ones)
+__device__ __forceinline__ int stack_num_items(const StackParams& p) {
+    return p.plane_list ? p.plane_list[0] * p.n_chunks : p.num_items;
+}
+__device__ __forceinline__ int stack_plane(const StackParams& p, int item, int& cj) {
+    const int pl = item / p.n_chunks;
+    cj = item - pl * p.n_chunks;
+    return p.plane_list ? p.plane_list[1 + pl] : pl;
+}
 
 // per-plane stack (Var-IO) with the index clamped into the weight image: the index arrays come straight from the caller
 __device__ __forceinline__ int stack_of(const StackParams& p, int bu) {
@@ -289,8 +300,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 
     bool z_prefetched = false;                          // the next item's first window is already in flight
     bool w_pending = false;                             // a weight blob load has been issued and not yet waited for
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int bu = item / p.n_chunks, cj = item - bu * p.n_chunks;
+    const int num_items = stack_num_items(p);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int cj;
+        const int bu = stack_plane(p, item, cj);
         const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
         const int stack = stack_of(p, bu);
@@ -489,9 +502,10 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             issue_mma(L::oPw1, 128 * 128, L::KP1, 128);
             if (k + 1 < nsteps) {
                 stage_z(b + kStepF + 1);                // prefetch overlaps layers 1-3 of this step
-            } else if (item + int(gridDim.x) < p.num_items) {   // last step: first window of the CTA's next item
+            } else if (item + int(gridDim.x) < num_items) {     // last step: first window of the CTA's next item
                 const int nitem = item + int(gridDim.x);
-                const int nbu = nitem / p.n_chunks, ncj = nitem - nbu * p.n_chunks;
+                int ncj;
+                const int nbu = stack_plane(p, nitem, ncj);
                 const int nstack = stack_of(p, nbu);
                 if (nstack == loaded_stack) {
                     const int nbu_a = p.pair_agg ? (nbu ^ 1) : nbu;

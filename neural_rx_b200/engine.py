@@ -23,6 +23,7 @@ NRX_MAX_DMRS = 4
 #: every symbol declared in include/nrx_b200.h
 EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
+    "nrx_set_skip_inactive",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_forward_host_async", "nrx_wait", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
     "nrx_plan_stack_chunks",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
@@ -80,6 +81,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_get_num_it.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
     lib.nrx_set_slots_per_pass.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    lib.nrx_set_skip_inactive.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_set_host_chunk.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]
     lib.nrx_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, f32p,
@@ -202,6 +204,10 @@ class NrxEngine:
         message MLP in their tail (two users); 5: warp-specialised pipelined stack kernels; 0/False: one kernel
         per SeparableConv2D layer (3, 4: round-1 experiments, only in -DNRX_EXPERIMENTAL_PLANS builds)."""
         self._check(self._lib.nrx_set_fused(self._h, int(fused)))
+
+    def set_skip_inactive(self, enable: bool) -> None:
+        """Do not compute the planes of inactive users (their outputs become zeros; active users bit-identical)."""
+        self._check(self._lib.nrx_set_skip_inactive(self._h, int(bool(enable))))
 
     def set_host_chunk(self, slots: int) -> None:
         """Slots per pipeline chunk of the host-buffer call (0 = default)."""

@@ -229,6 +229,32 @@ def test_active_user_masks(active):
     eng.close()
 
 
+@pytest.mark.parametrize("fused", [1, 5])
+@pytest.mark.parametrize("num_tx,active", [(2, [[1, 0], [0, 1], [1, 1], [0, 0], [1, 0]]), (3, [[1, 0, 1], [0, 1, 0], [1, 1, 1]])])
+def test_inactive_user_skipping(num_tx, active, fused):
+    """nrx_set_skip_inactive: the planes of inactive users are not computed (utils/neural_rx.py:192-204: their
+    messages are masked, so no active user depends on them).  Active users' outputs are bit-identical to the
+    reference behaviour (everything computed), inactive users' outputs are zeros; slots with a single active user
+    skip the message GEMMs (their messages are exactly zero)."""
+    import dataclasses
+    cfg = dataclasses.replace(get_config("nrx_rt"), max_num_tx=num_tx, dmrs_port_sets=[[0], [2], [1]][:num_tx])
+    cfg.validate()
+    weights, _ = get_weights(cfg, prefer_real=num_tx == 2, seed=3)
+    grid = build_grid(cfg, n_size_bwp=7)
+    act = np.asarray(active, np.float32)
+    sb = make_slots(cfg, grid, batch=act.shape[0], ebno_db=8.0, seed=23, active=act)
+    eng = _engine(cfg, weights, grid, fused=fused)
+    full = _run(eng, sb)
+    eng.set_skip_inactive(True)
+    skip = _run(eng, sb)
+    on = act > 0
+    for k in ("llr", "llr_grid", "h_hat_refined"):
+        assert np.array_equal(skip[k][on], full[k][on]), k
+        assert np.all(skip[k][~on] == 0), k
+    assert np.array_equal(skip["h_hat"], full["h_hat"])           # the LS estimate is an input-side quantity: all users
+    eng.close()
+
+
 @pytest.mark.parametrize("label,num_it", [("nrx_rt", 1), ("nrx_large", 3)])
 def test_num_it_truncation(label, num_it):
     """`num_it` may be lowered after training (utils/neural_rx.py:537-542)."""
