@@ -58,6 +58,10 @@ class NrxConfig:
     dmrs_symbols: Sequence[int] = (2, 11)   # type-A pos 2, additional_position 1, length 1
     dmrs_port_sets: Sequence[Sequence[int]] = ((0,), (2,))
     num_cdm_groups_without_data: int = 2
+    n_scid: int = 1                  # DMRS scrambling: the pilot VALUES follow from these four (config/nrx_rt.cfg:22-37)
+    dmrs_nid: Sequence[Sequence[int]] = ((1, 1), (1, 1))    # per transmitter: N_ID^0, N_ID^1
+    slot_number: int = 0
+    n_start_grid: int = 0
     # [neural_receiver]
     num_nrx_iter: int = 2
     num_nrx_iter_eval: int = 2
@@ -121,15 +125,30 @@ class NrxConfig:
             raise ValueError("num_units_agg / num_units_state need one entry per iteration")
 
 
+def _literal(expr: str):
+    """Value of one cfg entry.  The reference ``eval``s every value (utils/parameters.py:104-110), i.e. executes
+    whatever the file says; the cfg files only ever hold Python literals plus a dtype name (``tf.float32`` /
+    ``torch.float32``), so this parser accepts exactly that and nothing executable."""
+    import ast
+    import re
+    text = expr.strip()
+    m = re.fullmatch(r"(?:tf|torch)\.([A-Za-z_][A-Za-z0-9_]*)", text)
+    if m:
+        return getattr(_DtypeNamespace, m.group(1))
+    try:
+        return ast.literal_eval(text)
+    except (ValueError, SyntaxError) as exc:
+        raise ValueError(f"cfg value {expr!r} is not a Python literal") from exc
+
+
 def parse_cfg_text(text: str, training: bool = False) -> NrxConfig:
     """Parse a reference-format cfg (INI + Python expressions) into an :class:`NrxConfig`."""
     cp = configparser.RawConfigParser()
     cp.read_string(text)
-    ns = {"tf": _DtypeNamespace, "torch": _DtypeNamespace}
     raw = {}
     for section in cp.sections():
         for option in cp.options(section):
-            raw[option] = eval(cp.get(section, option), dict(ns))  # noqa: S307 (reference semantics)
+            raw[option] = _literal(cp.get(section, option))
     if not training:   # utils/parameters.py:118-127
         for key in ("n_size_bwp", "channel_norm"):
             if f"{key}_eval" in raw:
@@ -152,6 +171,10 @@ def parse_cfg_text(text: str, training: bool = False) -> NrxConfig:
         dmrs_symbols=tuple(dmrs_syms),
         dmrs_port_sets=tuple(tuple(p) for p in raw["dmrs_port_sets"]),
         num_cdm_groups_without_data=int(raw.get("num_cdm_groups_without_data", 2)),
+        n_scid=int(raw.get("n_scid", 1)),
+        dmrs_nid=tuple(tuple(int(v) for v in x) for x in raw.get("dmrs_nid", ((1, 1), (1, 1)))),
+        slot_number=int(raw.get("slot_number", 0)),
+        n_start_grid=int(raw.get("n_start_grid", 0)),
         num_nrx_iter=int(raw["num_nrx_iter"]),
         num_nrx_iter_eval=int(raw.get("num_nrx_iter_eval", raw["num_nrx_iter"])),
         d_s=int(raw["d_s"]),

@@ -76,10 +76,20 @@ def _comb_offset(port_set: Sequence[int]) -> int:
     return 0 if port in (0, 1, 4, 5) else 1
 
 
-def build_grid(cfg: NrxConfig, n_size_bwp: int | None = None, slot_number: int = 0,
-               n_id: int = 1, n_scid: int = 1, pilots: np.ndarray | None = None) -> PuschGrid:
+def build_grid(cfg: NrxConfig, n_size_bwp: int | None = None, slot_number: int | None = None,
+               n_id: int | None = None, n_scid: int | None = None, pilots: np.ndarray | None = None) -> PuschGrid:
     """Build the constant tables.  ``pilots`` ([U, n_dmrs*F] complex) overrides the 38.211 sequence
-    (any values are fine — only the zero / non-zero pattern shapes the tables)."""
+    (any values are fine — only the zero / non-zero pattern shapes the tables).  The DMRS scrambling
+    parameters default to the cfg's (``slot_number``, ``n_scid``, ``dmrs_nid[u][n_scid]`` per transmitter:
+    utils/parameters.py:140-192); the LS estimate divides by these pilot values, so they must be the
+    transmitter's."""
+    slot_number = cfg.slot_number if slot_number is None else slot_number
+    n_scid = cfg.n_scid if n_scid is None else n_scid
+    if cfg.n_start_grid != 0:
+        raise NotImplementedError("n_start_grid != 0: the pilot sequence offset of a shifted carrier grid is not implemented")
+    for ports in cfg.dmrs_port_sets[:cfg.max_num_tx]:
+        if len(ports) != 1:
+            raise NotImplementedError("one DMRS port (one layer) per transmitter only: multi-port sets are not implemented")
     F = 12 * (cfg.n_size_bwp if n_size_bwp is None else n_size_bwp)
     T = cfg.num_ofdm_symbols
     U = cfg.max_num_tx
@@ -92,10 +102,13 @@ def build_grid(cfg: NrxConfig, n_size_bwp: int | None = None, slot_number: int =
         pilots = np.zeros((U, nd * F), dtype=np.complex64)
         for u in range(U):
             delta = _comb_offset(cfg.dmrs_port_sets[u])
+            nid_u = n_id if n_id is not None else int(cfg.dmrs_nid[u % len(cfg.dmrs_nid)][n_scid])
+            # a_k = beta * w_f(k') * r(2n + k'), k = 4n + 2k' + Delta; TS 38.211 Table 6.4.1.1.3-1 (config type 1):
+            # w_f = [+1, +1] for the even ports 0, 2, 4, 6 and [+1, -1] for the odd ports 1, 3, 5, 7
+            w_f = np.where(np.arange(F // 2) % 2 == 0, 1.0, -1.0) if cfg.dmrs_port_sets[u][0] % 2 else np.ones(F // 2)
             for j, l in enumerate(syms):
-                r = dmrs_base_sequence(F, l, slot_number, n_id, n_scid, T)
-                # a_k = beta * w_f(k') * r(2n + k'), k = 4n + 2k' + Delta; w_f = +1 for ports 0 and 2
-                pilots[u, j * F + delta + 2 * np.arange(F // 2)] = (np.sqrt(2.0) * r).astype(np.complex64)
+                r = dmrs_base_sequence(F, l, slot_number, nid_u, n_scid, T)
+                pilots[u, j * F + delta + 2 * np.arange(F // 2)] = (np.sqrt(2.0) * w_f * r).astype(np.complex64)
     pilots = np.asarray(pilots, dtype=np.complex64)
     assert pilots.shape == (U, nd * F)
 
