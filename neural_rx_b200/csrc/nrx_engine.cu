@@ -378,14 +378,14 @@ int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const
     ap.U = U; ap.rows_per_bu = per_slot;
     ap.tiles_per_b = (per_slot + 127) / 128;
     ap.num_tiles = ap.tiles_per_b * bp;
-    const int cap = (U <= 2 ? 2 : 1) * e->num_sms;
+    const int cap = agg_ctas_per_sm(U) * e->num_sms;
     const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
     Timed t(e, st, NRX_K_AGG);
     switch (U) {
-        case 1: nrx_agg_kernel<1><<<grid, kThreads, agg_smem_bytes(1), st>>>(ap); break;
-        case 2: nrx_agg_kernel<2><<<grid, kThreads, agg_smem_bytes(2), st>>>(ap); break;
-        case 3: nrx_agg_kernel<3><<<grid, kThreads, agg_smem_bytes(3), st>>>(ap); break;
-        default: nrx_agg_kernel<4><<<grid, kThreads, agg_smem_bytes(4), st>>>(ap); break;
+        case 1: nrx_agg_kernel<1><<<grid, kAggThreads, agg_smem_bytes(1), st>>>(ap); break;
+        case 2: nrx_agg_kernel<2><<<grid, kAggThreads, agg_smem_bytes(2), st>>>(ap); break;
+        case 3: nrx_agg_kernel<3><<<grid, kAggThreads, agg_smem_bytes(3), st>>>(ap); break;
+        default: nrx_agg_kernel<4><<<grid, kAggThreads, agg_smem_bytes(4), st>>>(ap); break;
     }
     return NRX_OK;
 }
@@ -937,7 +937,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             nrx_prep_aerial_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
         } else {
             Timed t(e, st, NRX_K_PREP);
-            nrx_prep_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pp);
+            nrx_prep_kernel<<<bp * ((F + kPrepF - 1) / kPrepF), 256, 0, st>>>(pp);
         }
 
         // inactive-user skipping: ordered list of the active (slot, user) planes of this pass, built on the device

@@ -128,66 +128,84 @@ struct PrepParams {
     int F, U, N, n_pilot_slots, b0, bp;
 };
 
+// A block handles kPrepF subcarriers x 14 symbols of one slot.  The received grid is [N][T][F] (subcarrier
+// fastest) while the network's rows are subcarrier-major / symbol-fastest: the block first stages its
+// [N][T][kPrepF] patch of y in shared memory with coalesced loads along F, then every thread builds whole
+// output rows in (f, t) order from the patch (the LS gathers of a pilot slot hit its own FOCC block, which
+// lies inside the patch; anything outside falls back to a global load).
+constexpr int kPrepF = 16;
+
 __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
+    __shared__ float2 sy[7 * kT * kPrepF];                     // [a][t][fi]   (N <= 7)
+    __shared__ uint4 srow[kPrepF * kT * 4];                    // one user's z0 rows of the patch: contiguous in global memory
+    const int tiles_f = (p.F + kPrepF - 1) / kPrepF;
+    const int bl = blockIdx.x / tiles_f, f0 = (blockIdx.x - bl * tiles_f) * kPrepF;
+    const int nf = min(kPrepF, p.F - f0);
     const int per_slot = p.F * kT;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= p.bp * per_slot) return;
-    const int bl = idx / per_slot, rem = idx - bl * per_slot;
-    const int f = rem / kT, t = rem - f * kT;
     const int b = p.b0 + bl;
     const int N = p.N;
-    const float g = slot_gain(p.partial, b, 2 * N * per_slot);
     const float2* yb = p.y + size_t(b) * N * per_slot;
-    const int re = t * p.F + f;
-
-    float yre[8], yim[8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-        if (a < N) {
-            const float2 v = __ldg(yb + size_t(a) * per_slot + re);
-            yre[a] = v.x;
-            yim[a] = v.y;
-        }
+    for (int i = threadIdx.x; i < N * kT * kPrepF; i += 256) {
+        const int fi = i % kPrepF, at = i / kPrepF;            // at = a * T + t
+        if (fi < nf) sy[i] = __ldg(yb + size_t(at) * p.F + f0 + fi);
+    }
+    __syncthreads();
+    const float g = slot_gain(p.partial, b, 2 * N * per_slot);
+    auto y_at = [&](int a, int re) -> float2 {                 // re = t * F + f
+        const int t = re / p.F, f = re - t * p.F;
+        if (f >= f0 && f < f0 + nf) return sy[(a * kT + t) * kPrepF + (f - f0)];
+        return __ldg(yb + size_t(a) * per_slot + re);
+    };
     for (int u = 0; u < p.U; ++u) {
-        const int k = __ldg(p.nn_index + size_t(u) * per_slot + re);
-        const FoccEntry e = p.focc[size_t(u) * p.n_pilot_slots + k];
-        float hre[8], him[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-            if (a < N) {
-                const float2 y0 = __ldg(yb + size_t(a) * per_slot + e.src[0]);
-                const float2 y1 = __ldg(yb + size_t(a) * per_slot + e.src[1]);
-                hre[a] = y0.x * e.w[0].x - y0.y * e.w[0].y + (y1.x * e.w[1].x - y1.y * e.w[1].y);
-                him[a] = y0.x * e.w[0].y + y0.y * e.w[0].x + (y1.x * e.w[1].y + y1.y * e.w[1].x);
-            }
-        const float2 pe = *reinterpret_cast<const float2*>(p.pos_enc + ((size_t(u) * p.F + f) * kT + t) * 2);
-        __align__(16) __half row[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) row[c] = __float2half(0.f);
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-            if (a < N) {
-                row[a] = __float2half(yre[a] * g);
-                row[N + a] = __float2half(yim[a] * g);
-                row[2 * N + 2 + a] = __float2half(hre[a] * g);
-                row[3 * N + 2 + a] = __float2half(him[a] * g);
-            }
-        row[2 * N] = __float2half(pe.x);
-        row[2 * N + 1] = __float2half(pe.y);
-        const size_t prow = (size_t(bl) * p.U + u) * per_slot + rem;
-        uint4* dst = reinterpret_cast<uint4*>(p.z0 + prow * 32);
-        const uint4* srcv = reinterpret_cast<const uint4*>(row);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dst[c] = srcv[c];
-        if (p.h_ls) {
-            float* ho = p.h_ls + ((size_t(b) * p.U + u) * per_slot + rem) * (2 * N);
+      for (int i = threadIdx.x; i < nf * kT; i += 256) {
+            const int fi = i / kT, t = i - fi * kT;
+            const int f = f0 + fi;
+            const int rem = f * kT + t;
+            const int re = t * p.F + f;
+            const int k = __ldg(p.nn_index + size_t(u) * per_slot + re);
+            const FoccEntry e = p.focc[size_t(u) * p.n_pilot_slots + k];
+            float hre[8], him[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a)
                 if (a < N) {
-                    ho[a] = hre[a];
-                    ho[N + a] = him[a];
+                    const float2 y0 = y_at(a, e.src[0]);
+                    const float2 y1 = y_at(a, e.src[1]);
+                    hre[a] = y0.x * e.w[0].x - y0.y * e.w[0].y + (y1.x * e.w[1].x - y1.y * e.w[1].y);
+                    him[a] = y0.x * e.w[0].y + y0.y * e.w[0].x + (y1.x * e.w[1].y + y1.y * e.w[1].x);
                 }
-        }
+            const float2 pe = *reinterpret_cast<const float2*>(p.pos_enc + ((size_t(u) * p.F + f) * kT + t) * 2);
+            __align__(16) __half row[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) row[c] = __float2half(0.f);
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (a < N) {
+                    const float2 v = sy[(a * kT + t) * kPrepF + fi];
+                    row[a] = __float2half(v.x * g);
+                    row[N + a] = __float2half(v.y * g);
+                    row[2 * N + 2 + a] = __float2half(hre[a] * g);
+                    row[3 * N + 2 + a] = __float2half(him[a] * g);
+                }
+            row[2 * N] = __float2half(pe.x);
+            row[2 * N + 1] = __float2half(pe.y);
+            const uint4* srcv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) srow[i * 4 + ((c + i) & 3)] = srcv[c];      // rotated: conflict-free 64 B rows
+            if (p.h_ls) {
+                float* ho = p.h_ls + ((size_t(b) * p.U + u) * per_slot + rem) * (2 * N);
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (a < N) {
+                        ho[a] = hre[a];
+                        ho[N + a] = him[a];
+                    }
+            }
+      }
+      __syncthreads();
+      // the patch's rows of this user are one contiguous range of z0: coalesced 16-byte stores
+      uint4* dst = reinterpret_cast<uint4*>(p.z0 + ((size_t(bl) * p.U + u) * per_slot + size_t(f0) * kT) * 32);
+      for (int j = threadIdx.x; j < nf * kT * 4; j += 256) dst[j] = srow[(j & ~3) + (((j & 3) + (j >> 2)) & 3)];
+      __syncthreads();
     }
 }
 
@@ -566,87 +584,83 @@ struct alignas(64) AggParams {
 
 constexpr int kAggBlob = 8192 + 8192 + 256 + 256;
 constexpr int kAggMaxU = 4;
+constexpr int kAggThreads = 128;          // four warps = the four TMEM lane quadrants of one 128-row tile
 
-__host__ __device__ constexpr int agg_smem_bytes(int U) { return U * 32768 + ((kAggBlob + 127) / 128) * 128 + 1024; }
+__host__ __device__ constexpr int agg_smem_bytes(int U) { return U * 16384 + ((kAggBlob + 127) / 128) * 128 + 1024; }
+__host__ __device__ constexpr int agg_ctas_per_sm(int U) { return U <= 2 ? 4 : U == 3 ? 3 : 2; }
 
+// Small CTAs, many per SM: a tile is a chain of two GEMM round trips (issue -> commit -> wake, ~1.3 k cycles each)
+// with little arithmetic in between, so what pays is the number of tiles in flight per SM.  One CTA = 128 threads,
+// ONE shared-memory stage of U x 16 KB that holds, in turn, the state tiles (TMA, A of the first GEMM), the hidden
+// activations (A of the second GEMM) and the output staging, U x 64 TMEM columns: four CTAs per SM at U <= 2
+// (49 KB, 128 columns each).  Measured on B200 (nrx_large, batch 30): 0.656 ms per step against 0.678 ms for two
+// 256-thread CTAs with two stages; with 340 MB moved per launch (state in, messages out) that is 4.2 TB/s.
 template <int U>
-__global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(const __grid_constant__ AggParams p) {
+__global__ void __launch_bounds__(kAggThreads, agg_ctas_per_sm(U)) nrx_agg_kernel(const __grid_constant__ AggParams p) {
     constexpr uint32_t TM_COLS = (U <= 1) ? 64 : (U == 2) ? 128 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    // two stages of [U][128 rows][128 B]: the state tiles of a tile arrive by TMA while the previous tile is
-    // processed; a stage then holds, in turn, the state tiles (A of the first GEMM), the hidden activations (A of
-    // the second GEMM, written after the first has consumed the state) and the output staging
-    uint8_t* sW = smem + 2 * U * 16384;
+    uint8_t* sA = smem;
+    uint8_t* sH = sA;
+    uint8_t* sW = smem + U * 16384;
     const float* sB1 = reinterpret_cast<const float*>(sW + 16384);
     const float* sB2 = sB1 + 64;
-    __shared__ uint64_t bar_w, bar_mma, bar_ld[2];
+    __shared__ uint64_t bar_w, bar_mma, bar_ld;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_slot, TM_COLS);
-    auto load_tile = [&](int tile, int stage) {           // thread 0
+    auto load_tile = [&](int tile) {                      // thread 0
         const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
-        mbar_arrive_expect_tx(&bar_ld[stage], U * 16384);
+        mbar_arrive_expect_tx(&bar_ld, U * 16384);
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            tma_load_3d(smem + stage * (U * 16384) + u * 16384, &p.map_s, 0, rt * 128, b * U + u, &bar_ld[stage]);
+        for (int u = 0; u < U; ++u) tma_load_3d(sA + u * 16384, &p.map_s, 0, rt * 128, b * U + u, &bar_ld);
     };
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         mbar_init(&bar_mma, 1);
-        mbar_init(&bar_ld[0], 1);
-        mbar_init(&bar_ld[1], 1);
+        mbar_init(&bar_ld, 1);
         fence_mbar_init();
         mbar_arrive_expect_tx(&bar_w, kAggBlob);
         bulk_g2s(sW, p.wblob, kAggBlob, &bar_w);
-        if (int(blockIdx.x) < p.num_tiles) load_tile(blockIdx.x, 0);
+        if (int(blockIdx.x) < p.num_tiles) load_tile(blockIdx.x);
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = tmem_slot;
     mbar_wait(&bar_w, 0);
-    uint32_t ph_mma = 0;
-    const int q = warp & 3, hcol = warp >> 2;
-    const int r = q * 32 + lane;
+    uint32_t ph_mma = 0, ph_ld = 0;
+    const int r = warp * 32 + lane;                       // accumulator row of this thread
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_b, rt = tile - b * p.tiles_per_b;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
-        const int stage = it & 1;
-        uint8_t* sA = smem + stage * (U * 16384);
-        uint8_t* sH = sA;
-        if (tid == 0) {
-            // the other stage was last written by generic stores (hidden tile, staging) of the previous tile
-            if (tile + int(gridDim.x) < p.num_tiles) {
-                fence_proxy_async_smem();
-                load_tile(tile + gridDim.x, stage ^ 1);
-            }
-        }
-        // activity flags of the slot: fetched now, used in the output epilogue (the load used to sit there with its
-        // full latency)
+        const int next = tile + int(gridDim.x);
+        // activity flags of the slot: fetched now, used in the output epilogue
         float m[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) m[u] = __ldg(p.active_tx + b * U + u);
-        mbar_wait(&bar_ld[stage], (it >> 1) & 1);
+        mbar_wait(&bar_ld, ph_ld);
+        ph_ld ^= 1;
+        bool idle = false;
         if (p.skip_idle) {
             float n_on = 0.f;
 #pragma unroll
             for (int u = 0; u < U; ++u) n_on += m[u];
-            if (n_on <= 1.f) {                           // block-uniform: sum over the OTHER active users is empty
-                __syncthreads();                         // (every thread has passed the load barrier of this stage)
-                for (int i = tid; i < U * 128 * 8; i += kThreads) {
-                    const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
-                    if (rr < valid_rows && m[u] != 0.f)
-                        *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
-                            make_uint4(0, 0, 0, 0);
-                }
-                __syncthreads();
-                continue;
+            idle = n_on <= 1.f;                           // block-uniform: the sum over the OTHER active users is empty
+        }
+        if (idle) {
+            __syncthreads();                              // every thread has passed the load barrier
+            if (tid == 0 && next < p.num_tiles) load_tile(next);
+            for (int i = tid; i < U * 128 * 8; i += kAggThreads) {
+                const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
+                if (rr < valid_rows && m[u] != 0.f)
+                    *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
+                        make_uint4(0, 0, 0, 0);
             }
+            continue;
         }
         tc_fence_before_sync();
         __syncthreads();
@@ -661,24 +675,25 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after_sync();
-        // ---- hidden layer epilogue: ReLU(acc + b1) -> fp16 -> sH ------------------------------
+        // ---- hidden layer epilogue: ReLU(acc + b1) -> fp16 -> sH (the state tiles have been consumed) ------
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float v[32];
-            const int col = hcol * 32;
-            tmem_ld32(tmem_addr(tbase + u * 64, q * 32, col), v);
-            tmem_ld_wait();
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint32_t pk[4];
+            for (int col = 0; col < 64; col += 32) {
+                float v[32];
+                tmem_ld32(tmem_addr(tbase + u * 64, warp * 32, col), v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    pk[e] = pack_half2(fmaxf(v[j + 2 * e] + sB1[col + j + 2 * e], 0.f),
-                                       fmaxf(v[j + 2 * e + 1] + sB1[col + j + 2 * e + 1], 0.f));
-                const int cc = (col + j) >> 3;
-                st_shared_v4(sH + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        pk[e] = pack_half2(fmaxf(v[j + 2 * e] + sB1[col + j + 2 * e], 0.f),
+                                           fmaxf(v[j + 2 * e + 1] + sB1[col + j + 2 * e + 1], 0.f));
+                    const int cc = (col + j) >> 3;
+                    st_shared_v4(sH + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                }
             }
-        }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -700,42 +715,53 @@ __global__ void __launch_bounds__(kThreads, (U <= 2) ? 2 : 1) nrx_agg_kernel(con
             for (int u = 0; u < U; ++u) n_act += m[u];
             const float pm = fmaxf(n_act - 1.f, 0.f);
             const float scale = (pm == 0.f) ? 1.f : 1.f / pm;
-            const int col = hcol * 32;
-            float sp[U][32];
 #pragma unroll
-            for (int u = 0; u < U; ++u) tmem_ld32(tmem_addr(tbase + u * 64, q * 32, col), sp[u]);
-            tmem_ld_wait();
+            for (int col = 0; col < 64; col += 32) {
+                float sp[U][32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float tot = 0.f;
+                for (int u = 0; u < U; ++u) tmem_ld32(tmem_addr(tbase + u * 64, warp * 32, col), sp[u]);
+                tmem_ld_wait();
+                if (p.skip_idle) {                        // planes of skipped users hold stale data: select, never 0 * x
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    sp[u][j] = m[u] != 0.f ? (sp[u][j] + sB2[col + j]) * m[u] : 0.f;
-                    tot += sp[u][j];
+                    for (int u = 0; u < U; ++u)
+                        if (m[u] == 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sp[u][j] = -sB2[col + j];
+                        }
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) sp[u][j] = (tot - sp[u][j]) * scale;
+                for (int j = 0; j < 32; ++j) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        sp[u][j] = (sp[u][j] + sB2[col + j]) * m[u];
+                        tot += sp[u][j];
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) sp[u][j] = (tot - sp[u][j]) * scale;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const int cc = (col + j) >> 3;
+                        st_shared_v4(sA + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4),
+                                     make_uint4(pack_half2(sp[u][j], sp[u][j + 1]), pack_half2(sp[u][j + 2], sp[u][j + 3]),
+                                                pack_half2(sp[u][j + 4], sp[u][j + 5]), pack_half2(sp[u][j + 6], sp[u][j + 7])));
+                    }
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const int cc = (col + j) >> 3;
-                    st_shared_v4(sA + u * 16384 + r * 128 + ((cc ^ (r & 7)) << 4),
-                                 make_uint4(pack_half2(sp[u][j], sp[u][j + 1]), pack_half2(sp[u][j + 2], sp[u][j + 3]),
-                                            pack_half2(sp[u][j + 4], sp[u][j + 5]), pack_half2(sp[u][j + 6], sp[u][j + 7])));
-                }
         }
         tc_fence_before_sync();
         __syncthreads();
-        for (int i = tid; i < U * 128 * 8; i += kThreads) {
+        for (int i = tid; i < U * 128 * 8; i += kAggThreads) {
             const int u = i >> 10, rr = (i >> 3) & 127, cc = i & 7;
             if (rr < valid_rows)
                 *reinterpret_cast<uint4*>(p.abuf + ((size_t(b) * U + u) * p.rows_per_bu + r0 + rr) * 64 + cc * 8) =
                     ld_shared_v4(sA + u * 16384 + rr * 128 + ((cc ^ (rr & 7)) << 4));
         }
-        fence_proxy_async_smem();                // this stage is refilled by TMA (async proxy) two tiles later
+        fence_proxy_async_smem();                // the stage is refilled by TMA (async proxy): generic accesses first
         __syncthreads();
+        if (tid == 0 && next < p.num_tiles) load_tile(next);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -858,22 +884,29 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after_sync();
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-            float v[32];
-            const int col = hcol * 128 + c0;
-            tmem_ld32(tmem_addr(tbase, q * 32, col), v);
+        {   // hidden epilogue: 128 columns per thread in chunks of 32, the next chunk's TMEM load in flight during the
+            // arithmetic of the current one; bias as float4, ReLU fused into the fp16x2 conversion
+            float v[2][32];
+            tmem_ld32(tmem_addr(tbase, q * 32, hcol * 128), v[0]);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint32_t pk[4];
+            for (int c = 0; c < 4; ++c) {
+                const int col = hcol * 128 + c * 32;
+                if (c < 3) tmem_ld32(tmem_addr(tbase, q * 32, col + 32), v[(c + 1) & 1]);
+                const float(&x)[32] = v[c & 1];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    pk[e] = pack_half2(fmaxf(v[j + 2 * e] + sB1[col + j + 2 * e], 0.f),
-                                       fmaxf(v[j + 2 * e + 1] + sB1[col + j + 2 * e + 1], 0.f));
-                const int cc = (col + j) >> 3;
-                st_shared_v4(sH + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4),
-                             make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                for (int j = 0; j < 32; j += 8) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(sB1 + col + j);
+                    const float4 b1 = *reinterpret_cast<const float4*>(sB1 + col + j + 4);
+                    uint4 ov;
+                    ov.x = pack_relu_half2(x[j] + b0.x, x[j + 1] + b0.y);
+                    ov.y = pack_relu_half2(x[j + 2] + b0.z, x[j + 3] + b0.w);
+                    ov.z = pack_relu_half2(x[j + 4] + b1.x, x[j + 5] + b1.y);
+                    ov.w = pack_relu_half2(x[j + 6] + b1.z, x[j + 7] + b1.w);
+                    const int cc = (col + j) >> 3;
+                    st_shared_v4(sH + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4), ov);
+                }
+                if (c < 3) tmem_ld_wait();
             }
         }
         fence_proxy_async_smem();
