@@ -79,7 +79,24 @@ def full(path, out_md, out_json):
                 d.get(METRICS[3], 0), d.get(METRICS[4], 0), d.get(METRICS[5], 0), d.get(METRICS[6], 0),
                 d.get(METRICS[7], 0), d.get("launch__registers_per_thread", 0)))
             js[d["kernel"]] = {"dram_bytes_per_launch": rd + wr, "us": d.get("gpu__time_duration.sum", 0)}
-    json.dump(js, open(out_json, "w"), indent=1)
+    # keyed to the kernel sources the capture was taken on: bench.py only reports these traffic figures while the
+    # sources are unchanged (same hash as bench.source_hash())
+    import hashlib, os
+    h = hashlib.sha256()
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neural_rx_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    merged = {"source_hash": h.hexdigest()[:16], "kernels": js}
+    if os.path.exists(out_json):
+        try:
+            old = json.load(open(out_json))
+            if old.get("source_hash") == merged["source_hash"]:
+                old["kernels"].update(js)
+                merged = old
+        except Exception:
+            pass
+    json.dump(merged, open(out_json, "w"), indent=1)
     print(open(out_md).read())
 
 
