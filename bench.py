@@ -81,14 +81,16 @@ def _measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs.  Rank 0 samples its own GPU four
+    times a second; the other ranks do not sample (every nvidia-smi query goes through driver-wide locks: eight
+    ranks polling ten times a second were measured to cost the 8-GPU end-to-end run several percent)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self._stop, self._t, self.enabled = index, [], threading.Event(), None, enabled
 
     def _run(self):
         while not self._stop.is_set():
@@ -99,16 +101,18 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.25)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -308,7 +312,7 @@ def main():
         eng.forward(ys[i % NBUF], act, want=want, out=outs)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local_rank)      # samples through the timed region and the profiled / e2e repeats of it
+    clk = ClockSampler(local_rank, enabled=rank == 0)      # samples through the timed region and the profiled / e2e repeats of it
     clk.__enter__()
     e0.record()
     for i in range(args.steps):
@@ -385,7 +389,7 @@ def main():
              "frac_of_burst_peak": eng.flops_per_slot() * value / world / 1e12 / peak_burst}
 
     # ---- steady state: the same loop back to back for >= 5 s (a power-cap effect would show here) -------
-    sust_clk = ClockSampler(local_rank)
+    sust_clk = ClockSampler(local_rank, enabled=rank == 0)
     sust_clk.__enter__()
     n_sust = max(int(5.5 / max(ms / args.steps * 1e-3, 1e-6)), args.steps)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
