@@ -166,10 +166,23 @@ def from_list(cfg: NrxConfig, arrays: Sequence[np.ndarray]) -> NrxWeights:
     return NrxWeights(state_init, iterations, readout_llr, readout_chest)
 
 
+class _ArraysOnlyUnpickler(pickle.Unpickler):
+    """The reference ``pickle.load``s the weight file (utils/utils.py:53-70), i.e. runs whatever the file asks for.
+    A weight file is a list of NumPy arrays: this unpickler resolves only the globals NumPy's array pickles need
+    and refuses everything else, so a tampered file cannot execute code."""
+
+    _ALLOWED = {"_reconstruct", "ndarray", "dtype", "scalar", "_frombuffer"}
+
+    def find_class(self, module, name):
+        if module.split(".")[0] == "numpy" and name in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"weight file references {module}.{name}: only NumPy arrays are accepted")
+
+
 def load_weights(cfg: NrxConfig, model_path: str) -> NrxWeights:
     """``utils.load_weights`` equivalent: unpickle the list and bind it to the architecture."""
     with open(model_path, "rb") as f:
-        arrays = pickle.load(f)
+        arrays = _ArraysOnlyUnpickler(f).load()
     if not isinstance(arrays, (list, tuple)):
         raise ValueError("weight file does not hold a list of arrays")
     return from_list(cfg, arrays)

@@ -15,7 +15,7 @@ fork's torch port are broken), but its ``forward`` methods are
   copy_pytorch.py:311-321), the read-outs (:309-404), ``CGNN.forward`` (:544-595) and
   ``NeuralReceiverONNX.forward`` (:1773-1812, with ``NRPreprocessing.forward`` :1698-1711) on seeded
   4-PRB slots for nrx_rt (masks [1,1], [1,0], [0,1]; ``num_it`` = 1 and 2), nrx_rt_var_mcs (mixed
-  per-user MCS) and nrx_large_var_mcs_64qam_masking; it also executes ``post_process_llrs``
+  per-user MCS), nrx_large_var_mcs_64qam_masking, nrx_large, nrx_large_64qam and nrx_site_specific_large; it also executes ``post_process_llrs``
   (utils/onnx_utils.py:472-516), the LLR -> coded-bit order.  ``tests/test_ref_e2e_pins.py`` asserts
   ``cgnn_forward`` / ``receiver_forward`` / ``aerial_forward`` / ``demap_llrs`` <= 1e-5 against those
   outputs, and ``tests/test_gpu_parity.py`` compares the CUDA engine with the same

@@ -95,3 +95,31 @@ def test_receiver_requires_cuda_library_or_device():
             NeuralPUSCHReceiver(cfg, grid=grid)
     with pytest.raises(NotImplementedError):
         NeuralPUSCHReceiver(cfg, training=True, grid=grid)
+
+
+def test_weight_file_loader_accepts_arrays_only(tmp_path):
+    """The reference unpickles weight files without restriction (utils/utils.py:53-70); the loader here resolves
+    only the globals NumPy's array pickles need, so a file that asks for anything else is refused."""
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("executed",))
+
+    p = tmp_path / "evil_weights"
+    p.write_bytes(pickle.dumps([Evil()]))
+    with pytest.raises(pickle.UnpicklingError, match="only NumPy arrays"):
+        load_weights(get_config("nrx_rt"), str(p))
+    w = random_weights(get_config("nrx_rt"), seed=2)
+    q = tmp_path / "ok_weights"
+    q.write_bytes(pickle.dumps(w.to_list()))
+    assert load_weights(get_config("nrx_rt"), str(q)).num_params() == w.num_params()
+
+
+def test_cfg_values_are_literals_not_code():
+    """The reference eval()s every cfg value (utils/parameters.py:104-110); the parser here accepts Python literals
+    and the dtype names the cfg files use, nothing executable."""
+    from neural_rx_b200.config import _literal
+    assert _literal("[128, 128]") == [128, 128] and _literal("tf.float32") == "float32" and _literal("torch.float32") == "float32"
+    with pytest.raises(ValueError, match="not a Python literal"):
+        _literal("__import__('os').system('true')")

@@ -21,7 +21,8 @@ from oracle import nrx_oracle as O
 from tests.common import oracle_arch, oracle_net, weight_path
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_e2e_fixtures.npz")
-CASES = {"rt": "nrx_rt", "rt_it1": "nrx_rt", "varmcs": "nrx_rt_var_mcs", "masking": "nrx_large_var_mcs_64qam_masking"}
+CASES = {"rt": "nrx_rt", "rt_it1": "nrx_rt", "varmcs": "nrx_rt_var_mcs", "masking": "nrx_large_var_mcs_64qam_masking",
+         "large": "nrx_large", "large64": "nrx_large_64qam", "site": "nrx_site_specific_large"}
 TOL = 1e-5
 
 
