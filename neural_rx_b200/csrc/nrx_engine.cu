@@ -726,13 +726,17 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                 }
                 tab[size_t(u) * e->n_pilot_slots + k] = en;
             }
+        // resolve the nearest-pilot gather now: one entry per (user, RE) in the network's (f, t) row order
+        std::vector<FoccEntry> per_re(size_t(U) * TF);
         for (int u = 0; u < U; ++u)
-            for (int i = 0; i < TF; ++i) {
-                const int k = nn_index[size_t(u) * TF + i];
-                if (k < 0 || k >= e->n_pilot_slots) return bail(fail(NRX_ERR_INVALID, "nn_index out of range"));
-            }
-        if (cudaMalloc(&e->focc, tab.size() * sizeof(FoccEntry)) != cudaSuccess ||
-            cudaMemcpy(e->focc, tab.data(), tab.size() * sizeof(FoccEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
+            for (int f = 0; f < F; ++f)
+                for (int t = 0; t < kT; ++t) {
+                    const int k = nn_index[size_t(u) * TF + t * F + f];
+                    if (k < 0 || k >= e->n_pilot_slots) return bail(fail(NRX_ERR_INVALID, "nn_index out of range"));
+                    per_re[size_t(u) * TF + f * kT + t] = tab[size_t(u) * e->n_pilot_slots + k];
+                }
+        if (cudaMalloc(&e->focc, per_re.size() * sizeof(FoccEntry)) != cudaSuccess ||
+            cudaMemcpy(e->focc, per_re.data(), per_re.size() * sizeof(FoccEntry), cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMalloc(&e->nn_index, size_t(U) * TF * 4) != cudaSuccess ||
             cudaMemcpy(e->nn_index, nn_index, size_t(U) * TF * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMalloc(&e->pos_enc, size_t(U) * TF * 2 * 4) != cudaSuccess ||
@@ -922,8 +926,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
         PrepParams pp{};
         pp.y = static_cast<const float2*>(y);
         pp.partial = partial;
-        pp.nn_index = e->nn_index;
-        pp.focc = e->focc;
+        pp.focc_re = e->focc;
         pp.pos_enc = e->pos_enc;
         pp.z0 = z0;
         pp.h_ls = h_hat_ls;
@@ -934,10 +937,15 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             pa.partial = partial; pa.nn_prb = e->nn_prb; pa.pos_enc = pe_tab; pa.z0 = z0;
             pa.F = F; pa.U = U; pa.N = N; pa.n_pilots = e->aerial_pilots; pa.b0 = b0; pa.bp = bp;
             Timed t(e, st, NRX_K_PREP);
-            nrx_prep_aerial_kernel<<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
+            if (N == 4) nrx_prep_aerial_kernel<4><<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
+            else if (N == 2) nrx_prep_aerial_kernel<2><<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
+            else nrx_prep_aerial_kernel<0><<<(bp * per_slot + 255) / 256, 256, 0, st>>>(pa);
         } else {
             Timed t(e, st, NRX_K_PREP);
-            nrx_prep_kernel<<<bp * ((F + kPrepF - 1) / kPrepF), 256, 0, st>>>(pp);
+            const int pgrid_ = bp * ((F + kPrepF - 1) / kPrepF);
+            if (N == 4) nrx_prep_kernel<4><<<pgrid_, 256, 0, st>>>(pp);
+            else if (N == 2) nrx_prep_kernel<2><<<pgrid_, 256, 0, st>>>(pp);
+            else nrx_prep_kernel<0><<<pgrid_, 256, 0, st>>>(pp);
         }
 
         // inactive-user skipping: ordered list of the active (slot, user) planes of this pass, built on the device

@@ -112,16 +112,17 @@ __global__ void __launch_bounds__(1024) nrx_planes_kernel(const float* __restric
 //    (NeuralPUSCHReceiver.estimate_channel utils/neural_rx.py:1462-1514, copy_pytorch.py:899-911;
 //     CGNNOFDM.forward :832-839; StateInit concat :112-123)
 // =============================================================================================
-struct FoccEntry {     // LS estimate of pilot slot k of user u = sum_m y[src[m]] * w[m]
+struct alignas(16) FoccEntry {   // LS estimate of pilot slot k of user u = sum_m y[src[m]] * w[m]
     int32_t src[2];    // flat RE index t*F + f of the contributing pilot REs
     float2 w[2];       // 0.5 / pilot  (0 for a missing member)
+    int32_t pad[2];    // 32 bytes: two 16-byte loads
 };
 
 struct PrepParams {
     const float2* y;          // [B][N][T][F]
     const float* partial;     // [B][kPowerParts]
-    const int32_t* nn_index;  // [U][T*F]
-    const FoccEntry* focc;    // [U][n_pilot_slots]
+    const FoccEntry* focc_re; // [U][F*T]: the LS estimate that fills RE (f, t) of user u — nearest-pilot gather
+                              //   (utils/neural_rx.py:973-992) already resolved, rows in the network's (f, t) order
     const float* pos_enc;     // [U][F][T][2]
     __half* z0;               // [Bp*U*F*T][32]
     float* h_ls;              // [B][U][F][T][2N] or null
@@ -135,6 +136,10 @@ struct PrepParams {
 // lies inside the patch; anything outside falls back to a global load).
 constexpr int kPrepF = 16;
 
+// NT = compile-time number of receive antennas (0: taken from the parameters at run time).  With a run-time N the
+// indices of the 32-channel row (row[N + a], row[2N + 2 + a], ...) are dynamic and the row lives in local memory:
+// ~800 instructions per resource element; with NT known it is built in registers.
+template <int NT>
 __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
     __shared__ float2 sy[7 * kT * kPrepF];                     // [a][t][fi]   (N <= 7)
     __shared__ uint4 srow[kPrepF * kT * 4];                    // one user's z0 rows of the patch: contiguous in global memory
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
     const int nf = min(kPrepF, p.F - f0);
     const int per_slot = p.F * kT;
     const int b = p.b0 + bl;
-    const int N = p.N;
+    const int N = NT ? NT : p.N;
     const float2* yb = p.y + size_t(b) * N * per_slot;
     for (int i = threadIdx.x; i < N * kT * kPrepF; i += 256) {
         const int fi = i % kPrepF, at = i / kPrepF;            // at = a * T + t
@@ -162,8 +167,14 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
             const int f = f0 + fi;
             const int rem = f * kT + t;
             const int re = t * p.F + f;
-            const int k = __ldg(p.nn_index + size_t(u) * per_slot + re);
-            const FoccEntry e = p.focc[size_t(u) * p.n_pilot_slots + k];
+            FoccEntry e;
+            {
+                const uint4* ep = reinterpret_cast<const uint4*>(p.focc_re + size_t(u) * per_slot + rem);
+                const uint4 e0 = __ldg(ep), e1 = __ldg(ep + 1);
+                e.src[0] = int(e0.x); e.src[1] = int(e0.y);
+                e.w[0] = make_float2(__uint_as_float(e0.z), __uint_as_float(e0.w));
+                e.w[1] = make_float2(__uint_as_float(e1.x), __uint_as_float(e1.y));
+            }
             float hre[8], him[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a)
@@ -250,13 +261,14 @@ struct PrepAerialParams {
     int F, U, N, n_pilots, b0, bp;
 };
 
+template <int NT>
 __global__ void __launch_bounds__(256) nrx_prep_aerial_kernel(PrepAerialParams p) {
     const int per_slot = p.F * kT;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= p.bp * per_slot) return;
     const int bl = idx / per_slot, rem = idx - bl * per_slot;    // rem = f * T + t
     const int b = p.b0 + bl;
-    const int N = p.N;
+    const int N = NT ? NT : p.N;
     const float g = slot_gain(p.partial, b, 2 * N * per_slot);
     const float* yr = p.y_re + (size_t(b) * per_slot + rem) * N;
     const float* yi = p.y_im + (size_t(b) * per_slot + rem) * N;
