@@ -689,6 +689,11 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                 b1[n] = weight_arrays[i + 1][n];
                 b1[128 + n] = weight_arrays[ch + 1][n];
             }
+            for (int n = 0; n < 256; ++n) {   // bias as two fp16 rows of the W1 image (kRoBiasK)
+                const __half hi = __float2half(b1[n]), lo = __float2half(b1[n] - __half2float(hi));
+                *reinterpret_cast<__half*>(b + sw128_offset(n, kRoBiasK)) = hi;
+                *reinterpret_cast<__half*>(b + sw128_offset(n, kRoBiasK + 1)) = lo;
+            }
             float* b2 = b1 + 256;
             for (int n = 0; n < bits; ++n) b2[n] = weight_arrays[i + 3][n];
             for (int n = 0; n < n2; ++n) b2[16 + n] = weight_arrays[ch + 3][n];

@@ -803,43 +803,60 @@ struct ReadoutParams {
 };
 
 constexpr int kRoW1 = 256 * 128, kRoW2 = 4 * 32 * 128;
+// The first layer's bias rides in the GEMM: state channels 62 and 63 (always padding, d_s <= 60) are set to 1.0 when a
+// tile is staged and rows 62 / 63 of the W1 image hold the fp16 high and low halves of the bias (about 22 mantissa bits).
+constexpr int kRoBiasK = 62;
 constexpr int kRoBlob = kRoW1 + kRoW2 + 1024 + 128;
-constexpr int kRoSmem = 16384 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
+constexpr int kRoSmem = 32768 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
 
 // One CTA per SM.  Two per SM (state tile aliased onto the hidden tile, second accumulator onto the first: 106 KB,
 // 256 TMEM columns) were measured equal (0.220 vs 0.213 ms per 30-slot step): a tile is bound by the 256-column
-// accumulator read + bias/ReLU/pack + 64 KB hidden-tile write, not by the GEMM round trips.
+// accumulator read + bias/ReLU/pack + 64 KB hidden-tile write, not by the tensor pipe.
+// The tile loop is software-pipelined over two state tiles: tile t+1's first GEMM is issued right behind tile t's second
+// one (its accumulator has just been drained), so it runs under tile t's output epilogue and only the second GEMM's round
+// trip stays on the per-tile chain.  A change of LLR head between two tiles (Var-IO) falls back to the serial start.
 __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    uint8_t* sA = smem;                   // [128][128 B]
-    uint8_t* sH = smem + 16384;           // 4 slabs [128][128 B]
-    uint8_t* sW = smem + 16384 + 65536;
-    const float* sB1 = reinterpret_cast<const float*>(sW + kRoW1 + kRoW2);
-    const float* sB2 = sB1 + 256;
-    __shared__ uint64_t bar_w, bar_mma;
+    uint8_t* sA = smem;                   // 2 x [128][128 B]
+    uint8_t* sH = smem + 32768;           // 4 slabs [128][128 B]
+    uint8_t* sW = smem + 32768 + 65536;
+    const float* sB2 = reinterpret_cast<const float*>(sW + kRoW1 + kRoW2) + 256;
+    __shared__ uint64_t bar_w, bar_m1, bar_m2;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bar_w, 1);
-        mbar_init(&bar_mma, 1);
+        mbar_init(&bar_m1, 1);
+        mbar_init(&bar_m2, 1);
         fence_mbar_init();
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = tmem_slot;
-    uint32_t ph_w = 0, ph_mma = 0;
+    uint32_t ph_w = 0, ph_m1 = 0, ph_m2 = 0;
     int loaded_head = -1;
     const int q = warp & 3, hcol = warp >> 2;
     const int r = q * 32 + lane;
 
-    // next tile's state rows prefetched into registers while the current tile is processed
+    const int num_tiles = p.plane_list ? p.plane_list[0] * p.tiles_per_bu : p.num_tiles;
+    auto plane_of = [&](int tile) {
+        const int pl = tile / p.tiles_per_bu;
+        return p.plane_list ? p.plane_list[1 + pl] : pl;
+    };
+    auto head_of = [&](int bu) { return min(max(p.head_index ? p.head_index[bu] : p.default_head, 0), p.n_heads - 1); };
+
+    // state rows of the next TWO tiles travel in registers: with one tile (16 KB per SM) in flight the kernel was bound by
+    // the latency of these loads (0.18 -> 0.12 ms per 30-slot step with the loads stubbed out)
     constexpr int NV = 128 * 8 / kThreads;
-    uint4 pre[NV];
-    auto fetch = [&](int tile) {
+    uint4 pre[NV], pre2[NV];
+    auto fetch = [&](int tile, uint4 (&dst)[NV]) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) dst[v] = make_uint4(0, 0, 0, 0);
+        if (tile >= num_tiles) return;
         const int pl = tile / p.tiles_per_bu, rt = tile - pl * p.tiles_per_bu;
         const int bu = p.plane_list ? p.plane_list[1 + pl] : pl;
         const int r0 = rt * 128, valid_rows = min(128, p.rows_per_bu - r0);
@@ -847,37 +864,64 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
         for (int v = 0; v < NV; ++v) {
             const int i = tid + v * kThreads;
             const int rr = i >> 3, cc = i & 7;
-            pre[v] = make_uint4(0, 0, 0, 0);
+#ifndef NRX_RO_NOFETCH
             if (rr < valid_rows)
-                pre[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
+                dst[v] = __ldg(reinterpret_cast<const uint4*>(p.sbuf + (size_t(bu) * p.rows_per_bu + r0 + rr) * 64 + cc * 8));
+#endif
         }
     };
-    const int num_tiles = p.plane_list ? p.plane_list[0] * p.tiles_per_bu : p.num_tiles;
-    if (int(blockIdx.x) < num_tiles) fetch(blockIdx.x);
+    // writes the tile held in `pre` to a state buffer, moves `pre2` up and starts the loads of the tile after that one
+    auto stage = [&](uint8_t* dst, int tile_after) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int i = tid + v * kThreads;
+            const int rr = i >> 3, cc = i & 7;
+            uint4 x = pre[v];
+            if (cc == 7) x.w = 0x3C003C00u;   // channels 62, 63 = 1.0: they carry the first layer's bias (kRoBiasK)
+            st_shared_v4(dst + rr * 128 + ((cc ^ (rr & 7)) << 4), x);
+            pre[v] = pre2[v];
+        }
+        fetch(tile_after, pre2);
+    };
+    auto issue_first = [&](int buf) {
+#ifndef NRX_RO_NOMMA1
+        umma_gemm_k(tbase, smem_u32(sA + buf * 16384), 16384, smem_u32(sW), 256 * 128, 64, umma_idesc_f16(128, 256), false);
+#endif
+        umma_commit(&bar_m1);
+    };
+    fetch(blockIdx.x, pre);
+    fetch(blockIdx.x + gridDim.x, pre2);
+    bool first_issued = false;            // this tile's first GEMM was issued during the previous tile
+    int buf = 0;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int pl = tile / p.tiles_per_bu, rt = tile - pl * p.tiles_per_bu;
         const int bu = p.plane_list ? p.plane_list[1 + pl] : pl;
         const int r0 = rt * 128;
         const int valid_rows = min(128, p.rows_per_bu - r0);
-        const int head = min(max(p.head_index ? p.head_index[bu] : p.default_head, 0), p.n_heads - 1);
-        if (head != loaded_head) {
+        if (!first_issued) {
+            const int head = head_of(bu);
+            if (head != loaded_head) {
+                __syncthreads();          // the previous tile's output epilogue still reads the biases
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&bar_w, kRoBlob);
+                    bulk_g2s(sW, p.wblob + size_t(head) * kRoBlob, kRoBlob, &bar_w);
+                }
+                mbar_wait(&bar_w, ph_w);
+                ph_w ^= 1;
+                loaded_head = head;
+            }
+            stage(sA + buf * 16384, tile + 2 * int(gridDim.x));
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
             __syncthreads();
             if (tid == 0) {
-                mbar_arrive_expect_tx(&bar_w, kRoBlob);
-                bulk_g2s(sW, p.wblob + size_t(head) * kRoBlob, kRoBlob, &bar_w);
+                tc_fence_after_sync();
+                issue_first(buf);
             }
-            mbar_wait(&bar_w, ph_w);
-            ph_w ^= 1;
-            loaded_head = head;
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int i = tid + v * kThreads;
-            const int rr = i >> 3, cc = i & 7;
-            st_shared_v4(sA + rr * 128 + ((cc ^ (rr & 7)) << 4), pre[v]);
-        }
-        if (tile + int(gridDim.x) < num_tiles) fetch(tile + gridDim.x);
+        const int next = tile + int(gridDim.x);
+        const bool has_next = next < num_tiles;
         // demapped position of this thread's row: fetched now, used after the second GEMM (the load used to sit,
         // with its full latency, on the four warps of the output epilogue)
         int d_row = -1;
@@ -885,104 +929,116 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
             const int prow = r0 + r, f = prow / kT, t = prow - f * kT;
             d_row = __ldg(p.data_index + t * p.F + f);
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after_sync();
-            umma_gemm_k(tbase, smem_u32(sA), 16384, smem_u32(sW), 256 * 128, 64, umma_idesc_f16(128, 256), false);
-            umma_commit(&bar_mma);
-        }
-        mbar_wait(&bar_mma, ph_mma);
-        ph_mma ^= 1;
+        const bool pipe = has_next && head_of(plane_of(next)) == loaded_head;
+        mbar_wait(&bar_m1, ph_m1);
+        ph_m1 ^= 1;
         tc_fence_after_sync();
         {   // hidden epilogue: 128 columns per thread in chunks of 32, the next chunk's TMEM load in flight during the
-            // arithmetic of the current one; bias as float4, ReLU fused into the fp16x2 conversion
+            // conversion of the current one; the bias arrived through the GEMM, ReLU is fused into the fp16x2 conversion
             float v[2][32];
+#ifdef NRX_RO_NOLDTM
+            for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = float(tid + j);
+#else
             tmem_ld32(tmem_addr(tbase, q * 32, hcol * 128), v[0]);
             tmem_ld_wait();
+#endif
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col = hcol * 128 + c * 32;
+#ifndef NRX_RO_NOLDTM
                 if (c < 3) tmem_ld32(tmem_addr(tbase, q * 32, col + 32), v[(c + 1) & 1]);
+#endif
                 const float(&x)[32] = v[c & 1];
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(sB1 + col + j);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sB1 + col + j + 4);
                     uint4 ov;
-                    ov.x = pack_relu_half2(x[j] + b0.x, x[j + 1] + b0.y);
-                    ov.y = pack_relu_half2(x[j + 2] + b0.z, x[j + 3] + b0.w);
-                    ov.z = pack_relu_half2(x[j + 4] + b1.x, x[j + 5] + b1.y);
-                    ov.w = pack_relu_half2(x[j + 6] + b1.z, x[j + 7] + b1.w);
+                    ov.x = pack_relu_half2(x[j], x[j + 1]);
+                    ov.y = pack_relu_half2(x[j + 2], x[j + 3]);
+                    ov.z = pack_relu_half2(x[j + 4], x[j + 5]);
+                    ov.w = pack_relu_half2(x[j + 6], x[j + 7]);
                     const int cc = (col + j) >> 3;
+#ifdef NRX_RO_NOHST
+                    if (ov.x == 0x12345678u)
+#endif
                     st_shared_v4(sH + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4), ov);
                 }
+#ifndef NRX_RO_NOLDTM
                 if (c < 3) tmem_ld_wait();
+#endif
             }
         }
+        if (pipe) stage(sA + (buf ^ 1) * 16384, tile + 3 * int(gridDim.x));   // its last reader was the first GEMM of the tile before this one
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after_sync();
+#ifndef NRX_RO_NOMMA2
             umma_gemm_k(tbase + 256, smem_u32(sH), 16384, smem_u32(sW + kRoW1), 32 * 128, 256,
                         umma_idesc_f16(128, 32), false);
-            umma_commit(&bar_mma);
+#endif
+            umma_commit(&bar_m2);
+            if (pipe) issue_first(buf ^ 1);        // accumulator columns 0..255 were drained before the barrier above
         }
-        mbar_wait(&bar_mma, ph_mma);
-        ph_mma ^= 1;
+        first_issued = pipe;
+        if (pipe) buf ^= 1;
+        mbar_wait(&bar_m2, ph_m2);
+        ph_m2 ^= 1;
         tc_fence_after_sync();
-        if (warp < 4) {
-            float v[32];
-            tmem_ld32(tmem_addr(tbase + 256, q * 32, 0), v);
+        {   // output epilogue: warps 0..3 own the LLR columns 0..15, warps 4..7 the channel-estimate columns 16..31
+            float v[16];
+            tmem_ld16(tmem_addr(tbase + 256, q * 32, hcol * 16), v);
             tmem_ld_wait();
+#ifdef NRX_RO_NOSTG
+            if (r < valid_rows && v[0] == 1234.5f) {
+#else
             if (r < valid_rows) {
+#endif
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += sB2[j];
+                for (int j = 0; j < 16; ++j) v[j] += sB2[hcol * 16 + j];
                 const int prow = r0 + r;                      // row inside the (slot, user) grid
-                const int f = prow / kT, t = prow - f * kT;
                 const size_t grow = size_t(bu) * p.rows_per_bu + prow;
-                // vector stores for the shipped widths (2 / 4 / 6 bits per symbol): a row's values are contiguous
-                auto store_bits = [&](float* o) {
-                    if (p.vec && p.out_bits == 4) {
-                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else if (p.vec && p.out_bits == 2) {
-                        *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
-                    } else if (p.vec && p.out_bits == 6) {
-                        *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
-                        *reinterpret_cast<float2*>(o + 2) = make_float2(v[2], v[3]);
-                        *reinterpret_cast<float2*>(o + 4) = make_float2(v[4], v[5]);
-                    } else {
+                if (hcol == 0) {
+                    // vector stores for the shipped widths (2 / 4 / 6 bits per symbol): a row's values are contiguous
+                    auto store_bits = [&](float* o) {
+                        if (p.vec && p.out_bits == 4) {
+                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else if (p.vec && p.out_bits == 2) {
+                            *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+                        } else if (p.vec && p.out_bits == 6) {
+                            *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+                            *reinterpret_cast<float2*>(o + 2) = make_float2(v[2], v[3]);
+                            *reinterpret_cast<float2*>(o + 4) = make_float2(v[4], v[5]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < p.out_bits) o[j] = v[j];
+                        }
+                    };
+                    if (p.llr_grid) store_bits(p.llr_grid + grow * p.out_bits);
+                    if (p.llr && d_row >= 0) store_bits(p.llr + (size_t(bu) * p.n_data + d_row) * p.out_bits);
+                    if (p.llr_aerial) {
+                        const int bb = bu / p.U, uu = bu - bb * p.U;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (j < p.out_bits) o[j] = v[j];
+                            if (j < p.out_bits)
+                                p.llr_aerial[((size_t(bb) * p.out_bits + j) * p.U + uu) * p.rows_per_bu + prow] = -v[j];
                     }
-                };
-                if (p.llr_grid) store_bits(p.llr_grid + grow * p.out_bits);
-                if (p.llr && d_row >= 0) store_bits(p.llr + (size_t(bu) * p.n_data + d_row) * p.out_bits);
-                if (p.llr_aerial) {
-                    const int bb = bu / p.U, uu = bu - bb * p.U;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < p.out_bits)
-                            p.llr_aerial[((size_t(bb) * p.out_bits + j) * p.U + uu) * p.rows_per_bu + prow] = -v[j];
-                }
-                if (p.h_ref) {
+                } else if (p.h_ref) {
                     float* o = p.h_ref + grow * p.N2;
                     if (p.vec && p.N2 == 8) {
-                        *reinterpret_cast<float4*>(o) = make_float4(v[16], v[17], v[18], v[19]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[20], v[21], v[22], v[23]);
+                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (j < p.N2) o[j] = v[16 + j];
+                            if (j < p.N2) o[j] = v[j];
                     }
                 }
             }
         }
-        tc_fence_before_sync();
-        __syncthreads();
+        // no barrier here: the next hidden tile is written only after every thread has seen this tile's second GEMM
+        // complete, and the next second GEMM is issued behind the barrier that follows the hidden epilogue
     }
     tc_fence_before_sync();
     __syncthreads();
