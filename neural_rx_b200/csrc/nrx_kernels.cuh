@@ -806,6 +806,10 @@ constexpr int kRoW1 = 256 * 128, kRoW2 = 4 * 32 * 128;
 // The first layer's bias rides in the GEMM: state channels 62 and 63 (always padding, d_s <= 60) are set to 1.0 when a
 // tile is staged and rows 62 / 63 of the W1 image hold the fp16 high and low halves of the bias (about 22 mantissa bits).
 constexpr int kRoBiasK = 62;
+#ifndef NRX_RO_AHEAD
+#define NRX_RO_AHEAD 2
+#endif
+constexpr int kRoAhead = NRX_RO_AHEAD;   // state tiles in flight per CTA (registers); measured 2: 139 us, 3: 146, 4: 157
 constexpr int kRoBlob = kRoW1 + kRoW2 + 1024 + 128;
 constexpr int kRoSmem = 32768 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
 
@@ -849,10 +853,10 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
     };
     auto head_of = [&](int bu) { return min(max(p.head_index ? p.head_index[bu] : p.default_head, 0), p.n_heads - 1); };
 
-    // state rows of the next TWO tiles travel in registers: with one tile (16 KB per SM) in flight the kernel was bound by
-    // the latency of these loads (0.18 -> 0.12 ms per 30-slot step with the loads stubbed out)
+    // state rows of the next kRoAhead tiles travel in registers: with one tile (16 KB per SM) in flight the kernel was
+    // bound by the latency of these loads (0.18 -> 0.12 ms per 30-slot step with the loads stubbed out)
     constexpr int NV = 128 * 8 / kThreads;
-    uint4 pre[NV], pre2[NV];
+    uint4 pre[kRoAhead][NV];
     auto fetch = [&](int tile, uint4 (&dst)[NV]) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) dst[v] = make_uint4(0, 0, 0, 0);
@@ -870,18 +874,19 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
 #endif
         }
     };
-    // writes the tile held in `pre` to a state buffer, moves `pre2` up and starts the loads of the tile after that one
+    // writes the tile held in pre[0] to a state buffer, moves the others up and starts the loads of the tile after them
     auto stage = [&](uint8_t* dst, int tile_after) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const int i = tid + v * kThreads;
             const int rr = i >> 3, cc = i & 7;
-            uint4 x = pre[v];
+            uint4 x = pre[0][v];
             if (cc == 7) x.w = 0x3C003C00u;   // channels 62, 63 = 1.0: they carry the first layer's bias (kRoBiasK)
             st_shared_v4(dst + rr * 128 + ((cc ^ (rr & 7)) << 4), x);
-            pre[v] = pre2[v];
+#pragma unroll
+            for (int d = 0; d + 1 < kRoAhead; ++d) pre[d][v] = pre[d + 1][v];
         }
-        fetch(tile_after, pre2);
+        fetch(tile_after, pre[kRoAhead - 1]);
     };
     auto issue_first = [&](int buf) {
 #ifndef NRX_RO_NOMMA1
@@ -889,8 +894,8 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
 #endif
         umma_commit(&bar_m1);
     };
-    fetch(blockIdx.x, pre);
-    fetch(blockIdx.x + gridDim.x, pre2);
+#pragma unroll
+    for (int d = 0; d < kRoAhead; ++d) fetch(blockIdx.x + d * gridDim.x, pre[d]);
     bool first_issued = false;            // this tile's first GEMM was issued during the previous tile
     int buf = 0;
 
@@ -911,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
                 ph_w ^= 1;
                 loaded_head = head;
             }
-            stage(sA + buf * 16384, tile + 2 * int(gridDim.x));
+            stage(sA + buf * 16384, tile + kRoAhead * int(gridDim.x));
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncthreads();
@@ -967,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
 #endif
             }
         }
-        if (pipe) stage(sA + (buf ^ 1) * 16384, tile + 3 * int(gridDim.x));   // its last reader was the first GEMM of the tile before this one
+        if (pipe) stage(sA + (buf ^ 1) * 16384, tile + (kRoAhead + 1) * int(gridDim.x));   // its last reader was the first GEMM of the tile before this one
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
