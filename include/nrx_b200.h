@@ -225,7 +225,11 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
  *   nrx_debug_stack:     it >= 0: s_out = UpdateState_it(a, s) (residual included);
  *                        it <  0: s_out = StateInit_stack(z0), z0 rows of 32 channels [y | pe | h_ls | 0]
  *                        (execution plan 1 or 5 as set by nrx_set_fused)
- *   nrx_debug_readout:   llr_grid [B][U][F][T][out_bits], h_hat_refined [B][U][F][T][2*N_rx] from s */
+ *   nrx_debug_readout:   llr_grid [B][U][F][T][out_bits], h_hat_refined [B][U][F][T][2*N_rx] from s
+ *   nrx_debug_option:    NRX_OPT_AGG_PIPELINED (default 1): 0 runs the one-tile-per-CTA aggregation kernel also for
+ *                        two users (the pipelined kernel must reproduce it bit for bit) */
+#define NRX_OPT_AGG_PIPELINED 1
+int nrx_debug_option(nrx_engine* e, int32_t option, int32_t value);
 int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t batch, const void* s_f16,
                         const float* active_tx, void* a_f16);
 int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack, int32_t batch, const void* z0_f16,

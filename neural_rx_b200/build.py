@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libnrx_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "nrx_engine.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "nrx_kernels.cuh"), os.path.join(HERE, "csrc", "sm100_prims.cuh"),
            os.path.join(HERE, "csrc", "nrx_stack.cuh"), os.path.join(HERE, "csrc", "nrx_stack_pair.cuh"),
-           os.path.join(HERE, "csrc", "nrx_stack_tm.cuh"), os.path.join(HERE, "csrc", "nrx_stack_ws.cuh"),
+           os.path.join(HERE, "csrc", "nrx_stack_tm.cuh"), os.path.join(HERE, "csrc", "nrx_stack_ws.cuh"), os.path.join(HERE, "csrc", "nrx_agg_ws.cuh"),
            os.path.join(HERE, "..", "include", "nrx_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

@@ -22,6 +22,7 @@
 #include "nrx_stack_tm.cuh"
 #endif
 #include "nrx_stack_ws.cuh"
+#include "nrx_agg_ws.cuh"
 
 using namespace nrx;
 
@@ -93,6 +94,9 @@ struct nrx_engine {
     std::vector<SepLayer> init_layers;              // 3
     std::vector<std::vector<SepLayer>> upd_layers;  // [it][3]
     std::vector<uint8_t*> agg_blobs;                // [it]
+    struct AggBias { float v[128]; };               // host copies of the message-MLP biases [b1 | b2]: kernel parameters of
+    std::vector<AggBias> agg_bias;                  //   the pipelined two-user kernel (nrx_agg_ws.cuh)
+    int agg_pipelined = 1;                          // 0: nrx_agg_kernel<2> also for two users (cross-check, NRX_OPT_AGG_PIPELINED)
     uint8_t* readout_blob = nullptr;                // [n_io] heads
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
@@ -368,8 +372,9 @@ int make_window_map(CUtensorMap* m, const __half* base, int planes, int rows, in
 // box = one subcarrier (14 rows) of a (slot, user) plane
 int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) { return make_rows_map(m, base, planes, F * kT, kT); }
 
-int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const uint8_t* blob, const float* active,
+int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, int it, const float* active,
                int U, int per_slot, int bp, int skip_idle = 0) {
+    const uint8_t* blob = e->agg_blobs[it];
     AggParams ap{};
     ap.skip_idle = skip_idle;
     const int rc = make_rows_map(&ap.map_s, s, bp * U, per_slot, 128);
@@ -378,9 +383,18 @@ int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, const
     ap.U = U; ap.rows_per_bu = per_slot;
     ap.tiles_per_b = (per_slot + 127) / 128;
     ap.num_tiles = ap.tiles_per_b * bp;
+    Timed t(e, st, NRX_K_AGG);
+    if (U == 2 && e->agg_pipelined) {
+        AggWsParams wp{};
+        wp.a = ap;
+        if (const int rc2 = make_rows_map(&wp.map_a, a, bp * U, per_slot, 128)) return rc2;
+        std::memcpy(wp.b1, e->agg_bias[it].v, sizeof(wp.b1));
+        std::memcpy(wp.b2, e->agg_bias[it].v + 64, sizeof(wp.b2));
+        nrx_agg_ws_kernel<<<ap.num_tiles < e->num_sms ? ap.num_tiles : e->num_sms, kAggWsThreads, kAggWsSmem, st>>>(wp);
+        return NRX_OK;
+    }
     const int cap = agg_ctas_per_sm(U) * e->num_sms;
     const int grid = ap.num_tiles < cap ? ap.num_tiles : cap;
-    Timed t(e, st, NRX_K_AGG);
     switch (U) {
         case 1: nrx_agg_kernel<1><<<grid, kAggThreads, agg_smem_bytes(1), st>>>(ap); break;
         case 2: nrx_agg_kernel<2><<<grid, kAggThreads, agg_smem_bytes(2), st>>>(ap); break;
@@ -575,6 +589,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     const int widths_u[4] = {2 * d.d_s + 2, d.units_state[0], d.units_state[1], d.d_s};
     e->upd_layers.resize(d.num_it);
     e->agg_blobs.resize(d.num_it, nullptr);
+    e->agg_bias.resize(d.num_it);
     e->stack_upd_blobs.resize(d.num_it, nullptr);
 #ifdef NRX_EXPERIMENTAL_PLANS
     e->pair_upd_blobs.resize(d.num_it, nullptr);
@@ -589,6 +604,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
         float* b1 = reinterpret_cast<float*>(host.data() + 16384);
         for (int n = 0; n < d.units_agg; ++n) b1[n] = weight_arrays[idx + 1][n];
         for (int n = 0; n < d.d_s; ++n) b1[64 + n] = weight_arrays[idx + 3][n];
+        std::memcpy(e->agg_bias[it].v, b1, sizeof(e->agg_bias[it].v));
         if (cudaMalloc(&e->agg_blobs[it], kAggBlob) != cudaSuccess ||
             cudaMemcpy(e->agg_blobs[it], host.data(), kAggBlob, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(NRX_ERR_CUDA, "uploading aggregation weights failed"));
@@ -762,6 +778,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     acc(set_smem(nrx_agg_kernel<2>, agg_smem_bytes(2)));
     acc(set_smem(nrx_agg_kernel<3>, agg_smem_bytes(3)));
     acc(set_smem(nrx_agg_kernel<4>, agg_smem_bytes(4)));
+    acc(set_smem(nrx_agg_ws_kernel, kAggWsSmem));
     acc(set_smem(nrx_readout_kernel, kRoSmem));
     acc(set_smem(nrx_stack_kernel<kStackInit, false>, StackSmem<kStackInit>::kTotal));
     acc(set_smem(nrx_stack_kernel<kStackUpdate, false>, StackSmem<kStackUpdate>::kTotal));
@@ -834,6 +851,15 @@ int nrx_set_skip_inactive(nrx_engine* e, int32_t enable) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
     e->skip_inactive = enable != 0;
     return NRX_OK;
+}
+
+int nrx_debug_option(nrx_engine* e, int32_t option, int32_t value) {
+    if (!e) return fail(NRX_ERR_INVALID, "null engine");
+    if (option == NRX_OPT_AGG_PIPELINED) {
+        e->agg_pipelined = value != 0;
+        return NRX_OK;
+    }
+    return fail(NRX_ERR_INVALID, "nrx_debug_option: unknown option %d", int(option));
 }
 
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots) {
@@ -1010,7 +1036,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             kp.pair_agg = pair ? 1 : 0;
             for (int it = 0; it < e->num_it; ++it) {
                 if (!pair)
-                    if (const int rc = launch_agg(e, st, s_cur, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp, skip)) return rc;
+                    if (const int rc = launch_agg(e, st, s_cur, abuf, it, active_tx + size_t(b0) * U, U, per_slot, bp, skip)) return rc;
                 kp.a_in = pair ? sp_cur : abuf; kp.s_in = s_cur; kp.s_out = s_alt;
                 kp.sp_out = pair && it + 1 < e->num_it ? sp_alt : nullptr;
                 kp.wblob = e->stack_upd_blobs[it];
@@ -1061,7 +1087,7 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             sp.default_stack = 0;
             sp.n_stacks = 1;
             for (int it = 0; it < e->num_it; ++it) {
-                if (const int rc = launch_agg(e, st, sbuf, abuf, e->agg_blobs[it], active_tx + size_t(b0) * U, U, per_slot, bp)) return rc;
+                if (const int rc = launch_agg(e, st, sbuf, abuf, it, active_tx + size_t(b0) * U, U, per_slot, bp)) return rc;
                 const auto& L = e->upd_layers[it];
                 sp.src0 = abuf; sp.src1 = sbuf; sp.C0 = 64; sp.C1 = 64; sp.out = h1;
                 sp.wblob = L[0].blob; sp.blob_bytes = L[0].blob_bytes;
@@ -1349,7 +1375,7 @@ int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t ba
         return fail(NRX_ERR_INVALID, "nrx_debug_aggregate: bad argument");
     NRX_CUDA(cudaSetDevice(e->device));
     const int rc = launch_agg(e, static_cast<cudaStream_t>(cuda_stream), static_cast<const __half*>(s_f16), static_cast<__half*>(a_f16),
-                              e->agg_blobs[it], active_tx, e->d.max_num_tx, e->d.num_subcarriers * kT, batch);
+                              it, active_tx, e->d.max_num_tx, e->d.num_subcarriers * kT, batch, e->skip_inactive ? 1 : 0);
     if (rc) return rc;
     NRX_CUDA(cudaGetLastError());
     return NRX_OK;

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_forward_host_async", "nrx_wait", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
     "nrx_plan_stack_chunks",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
-    "nrx_debug_aggregate", "nrx_debug_stack", "nrx_debug_readout",
+    "nrx_debug_aggregate", "nrx_debug_stack", "nrx_debug_readout", "nrx_debug_option",
 )
 
 KERNEL_CLASSES = ("power", "prep", "sep_32x128", "sep_128x128", "sep_128x64_init_out",
@@ -104,6 +104,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_debug_aggregate.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
     lib.nrx_debug_stack.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
     lib.nrx_debug_readout.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]
+    lib.nrx_debug_option.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
     lib.nrx_last_error.restype = ctypes.c_char_p
     lib.nrx_version.restype = ctypes.c_char_p
     for name in EXPORTED_SYMBOLS:
@@ -386,6 +387,12 @@ class NrxEngine:
     def _stream(self, t):
         import torch
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+    OPT_AGG_PIPELINED = 1
+
+    def debug_option(self, option: int, value: int):
+        """Test switch (include/nrx_b200.h, nrx_debug_option)."""
+        self._check(self._lib.nrx_debug_option(self._h, int(option), int(value)))
 
     def debug_aggregate(self, it: int, s, active_tx):
         """s: fp16 CUDA [B,U,F,T,64] (state rows) -> a fp16 [B,U,F,T,64]."""

@@ -79,6 +79,32 @@ def test_aggregation_kernel(F, U, active):
 
 
 @pytest.mark.parametrize("F", WIDTHS)
+@pytest.mark.parametrize("skip", [0, 1])
+def test_pipelined_aggregation_equals_one_tile_kernel(F, skip):
+    """nrx_agg_ws_kernel (two users, TMA ring + warp roles) against nrx_agg_kernel<2>: same arithmetic, same bits;
+    slots with both / one / no active user, with and without inactive-user skipping, more tiles than CTAs at F = 3276."""
+    import torch
+    cfg, grid, weights, eng, rng = _setup(F, 2)
+    B = 7 if F >= 1584 else 5
+    act = np.asarray([[1, 1], [1, 0], [1, 1], [0, 1], [0, 0], [1, 1], [1, 1]][:B], np.float32)
+    rows = torch.as_tensor(_state_rows(_f16(1.5 * rng.standard_normal((B, 2, F, T, 56))), grid.pos_enc)).cuda()
+    act_d = torch.as_tensor(act).cuda()
+    eng.set_skip_inactive(bool(skip))
+    outs = []
+    for pipelined in (1, 0):
+        eng.debug_option(eng.OPT_AGG_PIPELINED, pipelined)
+        for it in (0, 1):
+            outs.append(eng.debug_aggregate(it, rows, act_d).cpu().numpy())
+    torch.cuda.synchronize()
+    for it in (0, 1):
+        new, old = outs[it], outs[2 + it]
+        keep = np.ones((B, 2), bool) if not skip else (act > 0)   # planes of skipped users are not written
+        assert np.array_equal(new[keep].view(np.uint16), old[keep].view(np.uint16))
+    assert not np.array_equal(outs[0], outs[1])
+    eng.close()
+
+
+@pytest.mark.parametrize("F", WIDTHS)
 def test_readout_kernel(F):
     import torch
     cfg, grid, weights, eng, rng = _setup(F)
