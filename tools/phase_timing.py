@@ -34,6 +34,8 @@ y = torch.as_tensor(np.repeat(sb.y, batch, axis=0)).cuda()
 act = torch.ones((batch, 2), device="cuda")
 eng = E.NrxEngine(cfg, w, grid)
 eng.set_fused(int(os.environ.get("NRX_FUSED", "1")))
+if os.environ.get("NRX_NUM_IT"):
+    eng.num_it = int(os.environ["NRX_NUM_IT"])   # e.g. 1: StateInit weighs as much as UpdateState in the totals
 lib = E.load_library()
 buf = (ctypes.c_ulonglong * 32)()
 for _ in range(2):
