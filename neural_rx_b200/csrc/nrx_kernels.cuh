@@ -806,12 +806,15 @@ constexpr int kRoW1 = 256 * 128, kRoW2 = 4 * 32 * 128;
 // The first layer's bias rides in the GEMM: state channels 62 and 63 (always padding, d_s <= 60) are set to 1.0 when a
 // tile is staged and rows 62 / 63 of the W1 image hold the fp16 high and low halves of the bias (about 22 mantissa bits).
 constexpr int kRoBiasK = 62;
+// TMEM columns: first accumulator [0, 256) fp32, hidden activations [256, 384) as fp16 pairs (the A operand of the second
+// GEMM is read from tensor memory: no 64 KB hidden tile in shared memory, no operand fetch for it), output [384, 416)
+constexpr uint32_t kRoHidCol = 256, kRoOutCol = 384;
 #ifndef NRX_RO_AHEAD
 #define NRX_RO_AHEAD 2
 #endif
 constexpr int kRoAhead = NRX_RO_AHEAD;   // state tiles in flight per CTA (registers); measured 2: 139 us, 3: 146, 4: 157
 constexpr int kRoBlob = kRoW1 + kRoW2 + 1024 + 128;
-constexpr int kRoSmem = 32768 + 65536 + ((kRoBlob + 127) / 128) * 128 + 1024;
+constexpr int kRoSmem = 32768 + ((kRoBlob + 127) / 128) * 128 + 1024;
 
 // One CTA per SM.  Two per SM (state tile aliased onto the hidden tile, second accumulator onto the first: 106 KB,
 // 256 TMEM columns) were measured equal (0.220 vs 0.213 ms per 30-slot step): a tile is bound by the 256-column
@@ -823,8 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* sA = smem;                   // 2 x [128][128 B]
-    uint8_t* sH = smem + 32768;           // 4 slabs [128][128 B]
-    uint8_t* sW = smem + 32768 + 65536;
+    uint8_t* sW = smem + 32768;
     const float* sB2 = reinterpret_cast<const float*>(sW + kRoW1 + kRoW2) + 256;
     __shared__ uint64_t bar_w, bar_m1, bar_m2;
     __shared__ uint32_t tmem_slot;
@@ -954,24 +956,18 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
                 if (c < 3) tmem_ld32(tmem_addr(tbase, q * 32, col + 32), v[(c + 1) & 1]);
 #endif
                 const float(&x)[32] = v[c & 1];
+                uint32_t hw[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint4 ov;
-                    ov.x = pack_relu_half2(x[j], x[j + 1]);
-                    ov.y = pack_relu_half2(x[j + 2], x[j + 3]);
-                    ov.z = pack_relu_half2(x[j + 4], x[j + 5]);
-                    ov.w = pack_relu_half2(x[j + 6], x[j + 7]);
-                    const int cc = (col + j) >> 3;
-#ifdef NRX_RO_NOHST
-                    if (ov.x == 0x12345678u)
+                for (int j = 0; j < 16; ++j) hw[j] = pack_relu_half2(x[2 * j], x[2 * j + 1]);
+#ifndef NRX_RO_NOHST
+                tmem_st16(tmem_addr(tbase + kRoHidCol, q * 32, hcol * 64 + c * 16), hw);
 #endif
-                    st_shared_v4(sH + (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4), ov);
-                }
 #ifndef NRX_RO_NOLDTM
                 if (c < 3) tmem_ld_wait();
 #endif
             }
         }
+        tmem_st_wait();
         if (pipe) stage(sA + (buf ^ 1) * 16384, tile + (kRoAhead + 1) * int(gridDim.x));   // its last reader was the first GEMM of the tile before this one
         fence_proxy_async_smem();
         tc_fence_before_sync();
@@ -979,8 +975,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
         if (tid == 0) {
             tc_fence_after_sync();
 #ifndef NRX_RO_NOMMA2
-            umma_gemm_k(tbase + 256, smem_u32(sH), 16384, smem_u32(sW + kRoW1), 32 * 128, 256,
-                        umma_idesc_f16(128, 32), false);
+            umma_gemm_k_ts(tbase + kRoOutCol, tbase + kRoHidCol, smem_u32(sW + kRoW1), 32 * 128, 256, umma_idesc_f16(128, 32));
 #endif
             umma_commit(&bar_m2);
             if (pipe) issue_first(buf ^ 1);        // accumulator columns 0..255 were drained before the barrier above
@@ -992,7 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) nrx_readout_kernel(ReadoutParams 
         tc_fence_after_sync();
         {   // output epilogue: warps 0..3 own the LLR columns 0..15, warps 4..7 the channel-estimate columns 16..31
             float v[16];
-            tmem_ld16(tmem_addr(tbase + 256, q * 32, hcol * 16), v);
+            tmem_ld16(tmem_addr(tbase + kRoOutCol, q * 32, hcol * 16), v);
             tmem_ld_wait();
 #ifdef NRX_RO_NOSTG
             if (r < valid_rows && v[0] == 1234.5f) {
