@@ -12,7 +12,7 @@ the host-buffer C-ABI call on page-locked host buffers (every step's H2D and D2H
 timed region; two asynchronous calls in flight, the serving pattern), plus ``roofline`` (dominant
 kernel, CUDA events around every launch, fraction of the burst AND of the sustained measured tensor
 peak), ``sustained`` (the same loop run back to back for >= 5 s), ``cpu_baseline`` (the oracle port on
-the host cores), ``latency_us`` (batch-1 p50 / p99 for nrx_rt and nrx_large: device-resident and through
+the host cores; rank 0 at N = 1 only, like the other single-GPU side measurements), ``latency_us`` (batch-1 p50 / p99 for nrx_rt and nrx_large: device-resident and through
 host buffers) and ``clocks``.
 
 ``--impl reference`` times the reference's own CPU path on the same workload: whole 30-slot steps on all
@@ -461,7 +461,10 @@ def main():
 
     if rank == 0:
         extra = {}
-        if not args.no_latency:
+        # single-GPU side measurements (batch-1 latency, nrx_rt, skipping, CPU baseline) run at N = 1 only: at N > 1 the
+        # other ranks would sit idle behind rank 0 for minutes (torchrun also pins OMP to one thread per rank)
+        single = world == 1
+        if single and not args.no_latency:
             # batch-1 latency uses plan 2 (message MLP fused into the stack kernels: 12 instead of 20
             # launches for nrx_large); throughput above uses plan 1
             lat = {}
@@ -496,6 +499,7 @@ def main():
         # reference does vs. only the active planes
         act_half = act.clone()
         act_half[:, 1] = 0
+        eng.set_fused(args.fused)
 
         def rate(n=max(args.steps // 2, 5)):
             for i in range(3):
@@ -508,13 +512,14 @@ def main():
             q1.record()
             torch.cuda.synchronize()
             return B * n / (q0.elapsed_time(q1) * 1e-3)
-        v_all = rate()
-        eng.set_skip_inactive(True)
-        v_skip = rate()
-        eng.set_skip_inactive(False)
-        extra["one_of_two_ues_active"] = {"all_planes_computed": v_all, "inactive_planes_skipped": v_skip, "unit": UNIT + " (one GPU)"}
+        if single:
+            v_all = rate()
+            eng.set_skip_inactive(True)
+            v_skip = rate()
+            eng.set_skip_inactive(False)
+            extra["one_of_two_ues_active"] = {"all_planes_computed": v_all, "inactive_planes_skipped": v_skip, "unit": UNIT + " (one GPU)"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if single and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             run = oracle_forward_timer(cfg, weights, grid, cores)
             chunk, _, _ = pick_cpu_mode(run, base)
