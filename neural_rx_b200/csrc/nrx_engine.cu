@@ -519,6 +519,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
     for (int m = 0; m < d.n_io; ++m)
         if (d.io_bits[m] < 1 || d.io_bits[m] > 16) return fail(NRX_ERR_UNSUPPORTED, "LLR head width must be <= 16");
     if (d.num_it < 1) return fail(NRX_ERR_INVALID, "num_it must be >= 1");
+    if (d.num_subcarriers > 65535) return fail(NRX_ERR_UNSUPPORTED, "num_subcarriers must be < 65536");
     if (d.num_subcarriers < 1 || d.focc_block < 1 || d.num_subcarriers % d.focc_block)
         return fail(NRX_ERR_INVALID, "num_subcarriers must be a positive multiple of focc_block");
     if (d.num_dmrs_symbols < 1 || d.num_dmrs_symbols > NRX_MAX_DMRS) return fail(NRX_ERR_INVALID, "bad DMRS symbol count");
@@ -740,21 +741,21 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
                         const float mag = pj[0] * pj[0] + pj[1] * pj[1];
                         if (mag == 0.f) continue;
                         if (n >= 2) return bail(fail(NRX_ERR_UNSUPPORTED, "more than two pilots per FOCC block"));
-                        en.src[n] = d.dmrs_symbols[j / F] * F + j % F;
+                        en.src[n] = (d.dmrs_symbols[j / F] << 16) | (j % F);
                         en.w[n] = make_float2(0.5f * pj[0] / mag, -0.5f * pj[1] / mag);   // 0.5 / p
                         ++n;
                     }
                 }
                 tab[size_t(u) * e->n_pilot_slots + k] = en;
             }
-        // resolve the nearest-pilot gather now: one entry per (user, RE) in the network's (f, t) row order
+        // resolve the nearest-pilot gather now: one entry per (user, RE), (t, f)-major like y
         std::vector<FoccEntry> per_re(size_t(U) * TF);
         for (int u = 0; u < U; ++u)
             for (int f = 0; f < F; ++f)
                 for (int t = 0; t < kT; ++t) {
                     const int k = nn_index[size_t(u) * TF + t * F + f];
                     if (k < 0 || k >= e->n_pilot_slots) return bail(fail(NRX_ERR_INVALID, "nn_index out of range"));
-                    per_re[size_t(u) * TF + f * kT + t] = tab[size_t(u) * e->n_pilot_slots + k];
+                    per_re[size_t(u) * TF + t * F + f] = tab[size_t(u) * e->n_pilot_slots + k];
                 }
         if (cudaMalloc(&e->focc, per_re.size() * sizeof(FoccEntry)) != cudaSuccess ||
             cudaMemcpy(e->focc, per_re.data(), per_re.size() * sizeof(FoccEntry), cudaMemcpyHostToDevice) != cudaSuccess ||

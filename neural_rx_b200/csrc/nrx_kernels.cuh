@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(1024) nrx_planes_kernel(const float* __restric
 //     CGNNOFDM.forward :832-839; StateInit concat :112-123)
 // =============================================================================================
 struct alignas(16) FoccEntry {   // LS estimate of pilot slot k of user u = sum_m y[src[m]] * w[m]
-    int32_t src[2];    // flat RE index t*F + f of the contributing pilot REs
+    int32_t src[2];    // t << 16 | f of the contributing pilot REs
     float2 w[2];       // 0.5 / pilot  (0 for a missing member)
     int32_t pad[2];    // 32 bytes: two 16-byte loads
 };
@@ -121,7 +121,7 @@ struct alignas(16) FoccEntry {   // LS estimate of pilot slot k of user u = sum_
 struct PrepParams {
     const float2* y;          // [B][N][T][F]
     const float* partial;     // [B][kPowerParts]
-    const FoccEntry* focc_re; // [U][F*T]: the LS estimate that fills RE (f, t) of user u — nearest-pilot gather
+    const FoccEntry* focc_re; // [U][T][F]: the LS estimate that fills RE (t, f) of user u — nearest-pilot gather
                               //   (utils/neural_rx.py:973-992) already resolved, rows in the network's (f, t) order
     const float* pos_enc;     // [U][F][T][2]
     __half* z0;               // [Bp*U*F*T][32]
@@ -139,10 +139,16 @@ constexpr int kPrepF = 16;
 // NT = compile-time number of receive antennas (0: taken from the parameters at run time).  With a run-time N the
 // indices of the 32-channel row (row[N + a], row[2N + 2 + a], ...) are dynamic and the row lives in local memory:
 // ~800 instructions per resource element; with NT known it is built in registers.
+constexpr int kPrepRowU4 = kT * 4 + 1;     // one subcarrier's 14 staged z0 rows (64 B each) + 16 B: threads of consecutive
+                                           //   subcarriers then write to consecutive 16-byte bank groups
+// Thread = one RE of the block's [14 symbols][16 subcarriers] patch, SUBCARRIER-fastest: the reads of the staged y patch,
+// of the per-RE table (stored (t, f)-major) and the staging writes are all bank-conflict-free and coalesced.  (With the
+// symbol-fastest mapping every read of the patch was a 14-way bank conflict — rows are 128 B apart — and the kernel ran
+// at 58 % shared-memory wavefront utilisation.)
 template <int NT>
 __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
     __shared__ float2 sy[7 * kT * kPrepF];                     // [a][t][fi]   (N <= 7)
-    __shared__ uint4 srow[kPrepF * kT * 4];                    // one user's z0 rows of the patch: contiguous in global memory
+    __shared__ uint4 srow[kPrepF * kPrepRowU4];                // one user's z0 rows of the patch: contiguous in global memory
     const int tiles_f = (p.F + kPrepF - 1) / kPrepF;
     const int bl = blockIdx.x / tiles_f, f0 = (blockIdx.x - bl * tiles_f) * kPrepF;
     const int nf = min(kPrepF, p.F - f0);
@@ -156,20 +162,20 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
     }
     __syncthreads();
     const float g = slot_gain(p.partial, b, 2 * N * per_slot);
-    auto y_at = [&](int a, int re) -> float2 {                 // re = t * F + f
-        const int t = re / p.F, f = re - t * p.F;
+    auto y_at = [&](int a, int tf) -> float2 {                 // tf = t << 16 | f
+        const int t = tf >> 16, f = tf & 0xFFFF;
         if (f >= f0 && f < f0 + nf) return sy[(a * kT + t) * kPrepF + (f - f0)];
-        return __ldg(yb + size_t(a) * per_slot + re);
+        return __ldg(yb + (size_t(a) * kT + t) * p.F + f);
     };
+    const int t = threadIdx.x / kPrepF, fi = threadIdx.x % kPrepF;
+    const bool on = t < kT && fi < nf;
+    const int f = f0 + fi;
     for (int u = 0; u < p.U; ++u) {
-      for (int i = threadIdx.x; i < nf * kT; i += 256) {
-            const int fi = i / kT, t = i - fi * kT;
-            const int f = f0 + fi;
+        if (on) {
             const int rem = f * kT + t;
-            const int re = t * p.F + f;
             FoccEntry e;
             {
-                const uint4* ep = reinterpret_cast<const uint4*>(p.focc_re + size_t(u) * per_slot + rem);
+                const uint4* ep = reinterpret_cast<const uint4*>(p.focc_re + size_t(u) * per_slot + t * p.F + f);
                 const uint4 e0 = __ldg(ep), e1 = __ldg(ep + 1);
                 e.src[0] = int(e0.x); e.src[1] = int(e0.y);
                 e.w[0] = make_float2(__uint_as_float(e0.z), __uint_as_float(e0.w));
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
             row[2 * N + 1] = __float2half(pe.y);
             const uint4* srcv = reinterpret_cast<const uint4*>(row);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) srow[i * 4 + ((c + i) & 3)] = srcv[c];      // rotated: conflict-free 64 B rows
+            for (int c = 0; c < 4; ++c) srow[fi * kPrepRowU4 + t * 4 + c] = srcv[c];
             if (p.h_ls) {
                 float* ho = p.h_ls + ((size_t(b) * p.U + u) * per_slot + rem) * (2 * N);
 #pragma unroll
@@ -211,15 +217,14 @@ __global__ void __launch_bounds__(256) nrx_prep_kernel(PrepParams p) {
                         ho[N + a] = him[a];
                     }
             }
-      }
-      __syncthreads();
-      // the patch's rows of this user are one contiguous range of z0: coalesced 16-byte stores
-      uint4* dst = reinterpret_cast<uint4*>(p.z0 + ((size_t(bl) * p.U + u) * per_slot + size_t(f0) * kT) * 32);
-      for (int j = threadIdx.x; j < nf * kT * 4; j += 256) dst[j] = srow[(j & ~3) + (((j & 3) + (j >> 2)) & 3)];
-      __syncthreads();
+        }
+        __syncthreads();
+        // the patch's rows of this user are one contiguous range of z0: coalesced 16-byte stores
+        uint4* dst = reinterpret_cast<uint4*>(p.z0 + ((size_t(bl) * p.U + u) * per_slot + size_t(f0) * kT) * 32);
+        for (int j = threadIdx.x; j < nf * kT * 4; j += 256) dst[j] = srow[j + j / (kT * 4)];
+        __syncthreads();
     }
 }
-
 // =============================================================================================
 // 2b. Aerial / TensorRT-shaped pre-processing (NRPreprocessing, utils/neural_rx.py:1614-1713):
 //     rx_slot_{real,imag} [B][F][T][N], LS estimates at the non-zero pilots h_hat_{real,imag}
