@@ -194,6 +194,13 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
  * item each; minimises waves x steps on num_sms persistent CTAs). */
 int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* chunks_per_plane);
 
+/* Host-only planning helper for the default ("balanced") work distribution of the fused stack kernels: the planes of
+ * a launch are laid end to end (planes x num_subcarriers subcarriers) and CTA `cta` of `num_ctas` walks the
+ * subcarriers [*first, *last) of that line, cut into one work item per plane it touches (every item recomputes a
+ * 4-subcarrier run-in).  The ranges partition the line; CTAs beyond (planes x num_subcarriers) / 5 get none. */
+int nrx_plan_stack_range(int32_t planes, int32_t num_subcarriers, int32_t num_ctas, int32_t cta, int64_t* first,
+                         int64_t* last);
+
 /* Algorithmic multiply-accumulates per user resource element for head `llr_head` at the current
  * num_it (sum of weight elements, biases excluded — SURVEY.md App. A.6). */
 int nrx_mac_per_pixel(const nrx_engine* e, int32_t llr_head, int64_t* macs);
@@ -227,8 +234,11 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
  *                        (execution plan 1 or 5 as set by nrx_set_fused)
  *   nrx_debug_readout:   llr_grid [B][U][F][T][out_bits], h_hat_refined [B][U][F][T][2*N_rx] from s
  *   nrx_debug_option:    NRX_OPT_AGG_PIPELINED (default 1): 0 runs the one-tile-per-CTA aggregation kernel also for
- *                        two users (the pipelined kernel must reproduce it bit for bit) */
+ *                        two users (the pipelined kernel must reproduce it bit for bit);
+ *                        NRX_OPT_STACK_BALANCED (default 1): 0 cuts every plane into nrx_plan_stack_chunks equal chunks
+ *                        instead of the balanced CTA ranges of nrx_plan_stack_range (same outputs bit for bit) */
 #define NRX_OPT_AGG_PIPELINED 1
+#define NRX_OPT_STACK_BALANCED 2
 int nrx_debug_option(nrx_engine* e, int32_t option, int32_t value);
 int nrx_debug_aggregate(nrx_engine* e, void* cuda_stream, int32_t it, int32_t batch, const void* s_f16,
                         const float* active_tx, void* a_f16);

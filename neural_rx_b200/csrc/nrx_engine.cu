@@ -97,6 +97,7 @@ struct nrx_engine {
     struct AggBias { float v[128]; };               // host copies of the message-MLP biases [b1 | b2]: kernel parameters of
     std::vector<AggBias> agg_bias;                  //   the pipelined two-user kernel (nrx_agg_ws.cuh)
     int agg_pipelined = 1;                          // 0: nrx_agg_kernel<2> also for two users (cross-check, NRX_OPT_AGG_PIPELINED)
+    int stack_balanced = 1;                         // 0: equal chunks per plane (choose_chunks) instead of balanced CTA ranges
     uint8_t* readout_blob = nullptr;                // [n_io] heads
     uint8_t* stack_init_blob = nullptr;             // fused StateInit stacks [n_io]
     std::vector<uint8_t*> stack_upd_blobs;          // fused UpdateState stack per iteration
@@ -402,6 +403,21 @@ int launch_agg(nrx_engine* e, cudaStream_t st, const __half* s, __half* a, int i
         default: nrx_agg_kernel<4><<<grid, kAggThreads, agg_smem_bytes(4), st>>>(ap); break;
     }
     return NRX_OK;
+}
+
+// Work distribution of an nrx_stack_kernel launch over `planes` planes: balanced CTA ranges (default) or equal chunks per
+// plane.  Returns the grid size.
+int set_stack_work(const nrx_engine* e, StackParams& kp, int planes, int F) {
+    kp.num_planes = planes;
+    if (e->stack_balanced) {
+        kp.n_chunks = 0;
+        kp.num_items = 0;
+        const long long g = (long long)planes * F / kMinSeg;
+        return int(g < 1 ? 1 : g > e->num_sms ? e->num_sms : g);
+    }
+    kp.n_chunks = choose_chunks(planes, F, e->num_sms);
+    kp.num_items = kp.n_chunks * planes;
+    return kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
 }
 
 // plan 5: one launch of the warp-specialised, pipelined stack kernel (nrx_stack_ws.cuh)
@@ -860,6 +876,10 @@ int nrx_debug_option(nrx_engine* e, int32_t option, int32_t value) {
         e->agg_pipelined = value != 0;
         return NRX_OK;
     }
+    if (option == NRX_OPT_STACK_BALANCED) {
+        e->stack_balanced = value != 0;
+        return NRX_OK;
+    }
     return fail(NRX_ERR_INVALID, "nrx_debug_option: unknown option %d", int(option));
 }
 
@@ -888,6 +908,15 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
 int nrx_plan_stack_chunks(int32_t planes, int32_t num_subcarriers, int32_t num_sms, int32_t* chunks_per_plane) {
     if (planes < 1 || num_subcarriers < 1 || num_sms < 1 || !chunks_per_plane) return fail(NRX_ERR_INVALID, "nrx_plan_stack_chunks: bad argument");
     *chunks_per_plane = choose_chunks(planes, num_subcarriers, num_sms);
+    return NRX_OK;
+}
+int nrx_plan_stack_range(int32_t planes, int32_t num_subcarriers, int32_t num_ctas, int32_t cta, int64_t* first, int64_t* last) {
+    if (planes < 1 || num_subcarriers < 1 || num_ctas < 1 || cta < 0 || cta >= num_ctas || !first || !last)
+        return fail(NRX_ERR_INVALID, "nrx_plan_stack_range: bad argument");
+    long long g0, g1;
+    stack_balanced_range((long long)planes * num_subcarriers, num_ctas, cta, g0, g1);
+    *first = g0;
+    *last = g1;
     return NRX_OK;
 }
 #ifdef NRX_EXPERIMENTAL_PLANS
@@ -992,10 +1021,8 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             kp.F = F; kp.U = U; kp.d_s = d.d_s;
             kp.n_stacks = d.n_io;
             kp.plane_list = plist;
-            kp.n_chunks = choose_chunks(BU, F, e->num_sms);
-            kp.num_items = kp.n_chunks * BU;
+            const int sgrid = set_stack_work(e, kp, BU, F);
             kp.pos_enc = pe_tab;
-            const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
             // two users: the message MLP of the next AggregateUserStates runs in the tail of each stack
             // and user u reads the other user's sp tensor directly (no aggregation kernel, no `a` tensor)
             const bool pair = U == 2 && e->fused == 2;
@@ -1395,8 +1422,7 @@ int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack,
     const int F = d.num_subcarriers, BU = batch * d.max_num_tx;
     StackParams kp{};
     kp.F = F; kp.U = d.max_num_tx; kp.d_s = d.d_s;
-    kp.n_chunks = choose_chunks(BU, F, e->num_sms);
-    kp.num_items = kp.n_chunks * BU;
+    const int sgrid = set_stack_work(e, kp, BU, F);
     kp.pos_enc = e->pos_enc;
     kp.z0 = static_cast<const __half*>(z0_f16);
     kp.a_in = static_cast<const __half*>(a_f16);
@@ -1405,7 +1431,6 @@ int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack,
     kp.wblob = init ? e->stack_init_blob : e->stack_upd_blobs[it];
     kp.default_stack = init ? stack : 0;
     kp.n_stacks = init ? d.n_io : 1;
-    const int sgrid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
     if (e->fused == 5) {
         const int rc = init ? launch_stack_ws<kStackInit>(e, st, kp, BU, F, e->init_bias[stack].v)
                             : launch_stack_ws<kStackUpdate>(e, st, kp, BU, F, e->upd_bias[it].v);

@@ -50,7 +50,8 @@ struct StackParams {
     const int32_t* stack_index;  // [BU] or null
     const float* pos_enc;        // [U][F][T][2]   (init)
     int F, U, d_s;
-    int n_chunks, num_items;
+    int n_chunks, num_items;     // n_chunks == 0: balanced ranges (nrx_stack_kernel only), see stack_begin
+    int num_planes;              // planes of the launch (all of them; with plane_list the active count is plane_list[0])
     int default_stack;
     int n_stacks;                // stacks in wblob: stack_index values are clamped to [0, n_stacks)
     const int32_t* plane_list;   // inactive-user skipping: [0] = number of active planes, [1 + i] = i-th one; or null
@@ -64,6 +65,56 @@ __device__ __forceinline__ int stack_plane(const StackParams& p, int item, int& 
     const int pl = item / p.n_chunks;
     cj = item - pl * p.n_chunks;
     return p.plane_list ? p.plane_list[1 + pl] : pl;
+}
+
+// Work distribution of nrx_stack_kernel.  n_chunks > 0: every plane is cut into n_chunks equal chunks, CTA b takes the
+// items b, b + grid, ... (choose_chunks picks n_chunks; the makespan is waves x steps of the longest chunk).
+// n_chunks == 0 ("balanced"): the launch's planes are laid end to end (W = planes x F subcarriers) and CTA b owns the
+// subcarriers [b W / G, (b + 1) W / G) of that line, G = min(grid, W / kMinSeg); where the range crosses a plane boundary
+// it becomes two (or more) items.  Every CTA then walks ~W / G + 4 subcarriers whatever the batch: at 30 slots x 2 users
+// x 1584 subcarriers on 148 CTAs 73-74 steps instead of 7 waves x 11 = 77.  Outputs do not depend on the cut (each item
+// recomputes its own 4-subcarrier run-in exactly).
+constexpr int kMinSeg = 5;
+struct StackCursor {
+    long long g, g_end;
+};
+__host__ __device__ __forceinline__ void stack_balanced_range(long long W, int grid, int cta, long long& g0, long long& g1) {
+    long long G = W / kMinSeg;
+    G = G < 1 ? 1 : G > grid ? grid : G;
+    if (cta >= G) { g0 = g1 = 0; return; }
+    g0 = cta * W / G;
+    g1 = (cta + 1) * W / G;
+}
+__device__ __forceinline__ StackCursor stack_begin(const StackParams& p) {
+    StackCursor c;
+    const int planes = p.plane_list ? p.plane_list[0] : p.num_planes;
+    if (p.n_chunks > 0) {
+        c.g = blockIdx.x;
+        c.g_end = (long long)planes * p.n_chunks;
+    } else {
+        stack_balanced_range((long long)planes * p.F, int(gridDim.x), int(blockIdx.x), c.g, c.g_end);
+    }
+    return c;
+}
+// next item of this CTA: plane bu, subcarriers [c0, c1); false when the CTA's work is done
+__device__ __forceinline__ bool stack_next(const StackParams& p, StackCursor& c, int& bu, int& c0, int& c1) {
+    if (c.g >= c.g_end) return false;
+    int pl;
+    if (p.n_chunks > 0) {
+        pl = int(c.g / p.n_chunks);
+        const int cj = int(c.g - (long long)pl * p.n_chunks);
+        c0 = int((long long)cj * p.F / p.n_chunks);
+        c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
+        c.g += gridDim.x;
+    } else {
+        pl = int(c.g / p.F);
+        c0 = int(c.g - (long long)pl * p.F);
+        const long long left = c.g_end - c.g;
+        c1 = left < p.F - c0 ? c0 + int(left) : p.F;
+        c.g += c1 - c0;
+    }
+    bu = p.plane_list ? p.plane_list[1 + pl] : pl;
+    return true;
 }
 
 // per-plane stack (Var-IO) with the index clamped into the weight image: the index arrays come straight from the caller
@@ -300,11 +351,9 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
 
     bool z_prefetched = false;                          // the next item's first window is already in flight
     bool w_pending = false;                             // a weight blob load has been issued and not yet waited for
-    const int num_items = stack_num_items(p);
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int cj;
-        const int bu = stack_plane(p, item, cj);
-        const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
+    StackCursor cur = stack_begin(p);
+    int bu, c0, c1;
+    while (stack_next(p, cur, bu, c0, c1)) {
         const int nsteps = (c1 - c0 + kRunIn + kStepF - 1) / kStepF;
         const int stack = stack_of(p, bu);
         if (stack != loaded_stack) {                   // block-uniform: first item or Var-IO switch
@@ -502,15 +551,13 @@ __global__ void __launch_bounds__(kStackThreads, 1) nrx_stack_kernel(StackParams
             issue_mma(L::oPw1, 128 * 128, L::KP1, 128);
             if (k + 1 < nsteps) {
                 stage_z(b + kStepF + 1);                // prefetch overlaps layers 1-3 of this step
-            } else if (item + int(gridDim.x) < num_items) {     // last step: first window of the CTA's next item
-                const int nitem = item + int(gridDim.x);
-                int ncj;
-                const int nbu = stack_plane(p, nitem, ncj);
-                const int nstack = stack_of(p, nbu);
-                if (nstack == loaded_stack) {
+            } else {                                    // last step: first window of the CTA's next item
+                StackCursor nx = cur;
+                int nbu, nc0, nc1;
+                if (stack_next(p, nx, nbu, nc0, nc1) && stack_of(p, nbu) == loaded_stack) {
                     const int nbu_a = p.pair_agg ? (nbu ^ 1) : nbu;
                     const bool na_live = !p.pair_agg || p.active_tx[nbu_a] != 0.f;
-                    stage_z_of(nbu, nbu_a, na_live, int((long long)ncj * p.F / p.n_chunks) - kRunIn + 1);
+                    stage_z_of(nbu, nbu_a, na_live, nc0 - kRunIn + 1);
                     z_prefetched = true;
                 }
             }

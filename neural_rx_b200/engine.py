@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "nrx_create", "nrx_destroy", "nrx_set_num_it", "nrx_get_num_it", "nrx_set_slots_per_pass", "nrx_set_fused", "nrx_set_host_chunk",
     "nrx_set_skip_inactive",
     "nrx_workspace_bytes", "nrx_forward", "nrx_forward_host", "nrx_forward_host_async", "nrx_wait", "nrx_set_aerial_dmrs", "nrx_forward_aerial", "nrx_launches_per_forward",
-    "nrx_plan_stack_chunks",
+    "nrx_plan_stack_chunks", "nrx_plan_stack_range",
     "nrx_mac_per_pixel", "nrx_set_profiling", "nrx_get_profile", "nrx_last_error", "nrx_version",
     "nrx_debug_aggregate", "nrx_debug_stack", "nrx_debug_readout", "nrx_debug_option",
 )
@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     lib.nrx_launches_per_forward.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
     i32o = ctypes.POINTER(ctypes.c_int32)
     lib.nrx_plan_stack_chunks.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i32o]
+    i64o = ctypes.POINTER(ctypes.c_int64)
+    lib.nrx_plan_stack_range.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64o, i64o]
     lib.nrx_mac_per_pixel.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]
     lib.nrx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.nrx_get_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
@@ -389,6 +391,7 @@ class NrxEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
     OPT_AGG_PIPELINED = 1
+    OPT_STACK_BALANCED = 2
 
     def debug_option(self, option: int, value: int):
         """Test switch (include/nrx_b200.h, nrx_debug_option)."""

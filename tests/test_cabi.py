@@ -63,3 +63,37 @@ def test_stack_work_split_without_device(lib, planes, F):
         return -(-planes * nn // sms) * steps
     assert cost(n) == min(cost(nn) for nn in range(1, min(max(F // 5, 1), 512) + 1))
     assert lib.nrx_plan_stack_chunks(0, F, sms, None) == 1                 # NRX_ERR_INVALID
+
+
+@pytest.mark.parametrize("planes,F,ctas", [(60, 1584, 148), (2, 1584, 148), (2, 48, 148), (7, 12, 148), (1, 3, 148), (120, 3276, 148), (59, 1584, 132)])
+def test_stack_balanced_ranges_without_device(lib, planes, F, ctas):
+    """Default work distribution of the fused stack kernels (nrx_plan_stack_range): the CTA ranges partition the
+    planes x F line in order, empty ranges only at the end, no range shorter than 5 subcarriers unless the whole
+    launch is, and the longest CTA walk (steps of 9 subcarriers, 4-subcarrier run-in per item) never exceeds what
+    equal chunks per plane (nrx_plan_stack_chunks) cost."""
+    W = planes * F
+    a, b = ctypes.c_int64(), ctypes.c_int64()
+    pos, worst, seen_empty = 0, 0, False
+    for c in range(ctas):
+        assert lib.nrx_plan_stack_range(planes, F, ctas, c, ctypes.byref(a), ctypes.byref(b)) == 0
+        if a.value == b.value:
+            seen_empty = True
+            continue
+        assert not seen_empty and a.value == pos and b.value > a.value
+        assert b.value - a.value >= min(5, W)
+        steps, g = 0, a.value
+        while g < b.value:                                  # items: one per plane touched
+            c0 = g % F
+            c1 = min(F, c0 + b.value - g)
+            steps += -(-(c1 - c0 + 4) // 9)
+            g += c1 - c0
+        worst = max(worst, steps)
+        pos = b.value
+    assert pos == W
+    n = ctypes.c_int32()
+    assert lib.nrx_plan_stack_chunks(planes, F, ctas, ctypes.byref(n)) == 0
+    uniform = -(-planes * n.value // ctas) * -(-(-(-F // n.value) + 4) // 9)
+    assert worst <= uniform
+    if (planes, F, ctas) == (60, 1584, 148):
+        assert uniform == 77 and worst <= 74
+    assert lib.nrx_plan_stack_range(planes, F, ctas, ctas, ctypes.byref(a), ctypes.byref(b)) == 1     # NRX_ERR_INVALID

@@ -255,6 +255,34 @@ def test_inactive_user_skipping(num_tx, active, fused):
     eng.close()
 
 
+@pytest.mark.parametrize("label,n_prb,active", [
+    ("nrx_rt", 3, [[1, 1], [1, 1], [1, 1]]),                      # 6 planes x 36 subcarriers: ranges of 5 straddle planes
+    ("nrx_rt", 11, [[1, 1], [1, 0], [0, 1], [1, 1], [0, 0], [1, 1], [1, 1]]),
+    ("nrx_large", 132, [[1, 1], [1, 1], [1, 0]]),                 # 6 (5 with skipping) planes x 1584 on 148 CTAs
+    ("nrx_rt", 273, [[1, 1]]),
+])
+@pytest.mark.parametrize("skip", [0, 1])
+def test_balanced_stack_ranges_equal_uniform_chunks(label, n_prb, active, skip):
+    """Default work distribution of the fused stack kernels (balanced CTA ranges over the planes laid end to end,
+    nrx_plan_stack_range; with inactive-user skipping over the ACTIVE planes only, counted on the device) against
+    equal chunks per plane (NRX_OPT_STACK_BALANCED = 0): every output bit for bit — an item's run-in recomputes the
+    values its neighbour produced, so the cut must not show."""
+    cfg = get_config(label)
+    weights, _ = get_weights(cfg)
+    grid = build_grid(cfg, n_size_bwp=n_prb)
+    act = np.asarray(active, np.float32)
+    sb = make_slots(cfg, grid, batch=act.shape[0], ebno_db=7.0, seed=29, active=act)
+    eng = _engine(cfg, weights, grid, fused=1)
+    eng.set_skip_inactive(bool(skip))
+    bal = _run(eng, sb)
+    eng.debug_option(eng.OPT_STACK_BALANCED, 0)
+    uni = _run(eng, sb)
+    for k in ("llr", "llr_grid", "h_hat_refined", "h_hat"):
+        assert np.array_equal(bal[k], uni[k]), k
+    assert np.any(bal["llr"] != 0) or not act.any()
+    eng.close()
+
+
 @pytest.mark.parametrize("label,num_it", [("nrx_rt", 1), ("nrx_large", 3)])
 def test_num_it_truncation(label, num_it):
     """`num_it` may be lowered after training (utils/neural_rx.py:537-542)."""

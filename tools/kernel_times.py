@@ -12,7 +12,9 @@ y = torch.as_tensor(np.repeat(sb.y, 30, axis=0)).cuda(); act = torch.ones((30, 2
 eng = E.NrxEngine(cfg, w, grid)
 for _ in range(3): eng.forward(y, act, want=("llr",))
 torch.cuda.synchronize(); eng.set_profiling(True); eng.get_profile()
-for want in (("llr", "h_hat_refined"), ("llr", "h_hat_refined", "h_hat")):
-    for _ in range(10): eng.forward(y, act, want=want)
-    torch.cuda.synchronize(); pr = eng.get_profile()
-    print(want, {k: round(v["ms"] / max(v["launches"], 1) * 1e3, 1) for k, v in pr.items() if v["launches"]})
+for balanced in (1, 0):
+    eng.debug_option(eng.OPT_STACK_BALANCED, balanced)
+    for want in (("llr", "h_hat_refined"), ("llr", "h_hat_refined", "h_hat")):
+        for _ in range(10): eng.forward(y, act, want=want)
+        torch.cuda.synchronize(); pr = eng.get_profile()
+        print("balanced" if balanced else "uniform", want, {k: round(v["ms"] / max(v["launches"], 1) * 1e3, 1) for k, v in pr.items() if v["launches"]})
