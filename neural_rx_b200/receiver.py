@@ -6,10 +6,13 @@ Mirrors (names, argument meaning, error behaviour):
 * ``NeuralPUSCHReceiver(sys_parameters, training=False)`` — ``utils/neural_rx.py:1384-1603``;
   inference call ``receiver((y, active_tx), no, mcs_arr_eval=[0], mcs_ue_mask_eval=None)``
   (``:1544-1603``; ``no`` never influences the LLRs, it only fed the discarded LS error variance).
-  The reference then runs Sionna's ``TBDecoder`` on the LLRs (``:1600``); the transport-block
-  chain is third-party code outside this hot path, so the first tuple element
-  is the LLR tensor ``[B, U, n_coded_bits]`` that the decoder would consume and the CRC status
-  is ``None``.
+  The reference then runs Sionna's ``TBDecoder`` on the LLRs (``:1600``).  The transport-block chain is
+  third-party code outside the hot path: ``neural_rx_b200/tb.py`` restates it for the BLER
+  harness, and it needs the TS 38.212 base-graph tables, which this image does not hold.  Default
+  (``tb_decoding="auto"``): when the tables are found (Sionna installed, or ``$NRX_LDPC_BG_DIR``) the call returns
+  ``(b_hat, h_hat_refined, h_hat, tb_crc_status)`` like the reference; otherwise the first element is the LLR
+  tensor ``[B, U, n_coded_bits]`` the decoder would consume and the CRC status is ``None``.
+  ``tb_decoding="standin"`` decodes with the structural stand-in code (harness / tests), ``"off"`` never decodes.
 * ``CGNNOFDM`` LLR-level call — ``utils/neural_rx.py:813-881``:
   ``receiver.llrs((y, active_tx), mcs_arr_eval, mcs_ue_mask_eval)`` -> ``(llr, h_hat_refined)``.
 * ``num_it`` property with the reference's assertion (``:532-542``).
@@ -33,7 +36,8 @@ from .weights import NrxWeights, load_weights as _load_weight_file, random_weigh
 class NeuralPUSCHReceiver:
     def __init__(self, sys_parameters: Union[NrxConfig, str], training: bool = False,
                  weights: Optional[NrxWeights] = None, grid: Optional[PuschGrid] = None,
-                 device: int = 0, **kwargs):
+                 device: int = 0, tb_decoding: str = "auto", num_bp_iter: int = 20, cn_type: str = "boxplus",
+                 n_rntis: Sequence[int] = (1, 1), n_ids: Sequence[int] = (1, 1), **kwargs):
         if training:
             raise NotImplementedError("the B200 engine implements the inference path only")
         cfg = get_config(sys_parameters) if isinstance(sys_parameters, str) else sys_parameters
@@ -43,6 +47,24 @@ class NeuralPUSCHReceiver:
         self._device = device
         self._num_it = cfg.num_nrx_iter_eval
         self._engine: Optional[NrxEngine] = None
+        # transport-block decoders, one per supported MCS (utils/neural_rx.py:1402-1413)
+        if tb_decoding not in ("auto", "3gpp", "standin", "off"):
+            raise ValueError("tb_decoding must be 'auto', '3gpp', 'standin' or 'off'")
+        self._tb_encoders, self._tb_decoders = [], []
+        if tb_decoding != "off":
+            from . import tb as _tb
+            U = self._grid.num_tx
+            rn = (list(n_rntis) * U)[:U]
+            ni = (list(n_ids) * U)[:U]
+            try:
+                for i in range(cfg.num_mcss_supported):
+                    enc = _tb.pusch_tb_encoder(cfg, self._grid, i, rn, ni, "3gpp" if tb_decoding == "auto" else tb_decoding)
+                    self._tb_encoders.append(enc)
+                    self._tb_decoders.append(_tb.TBDecoder(enc, num_bp_iter=num_bp_iter, cn_type=cn_type))
+            except _tb.BaseGraphUnavailable:
+                if tb_decoding == "3gpp":
+                    raise
+                self._tb_encoders, self._tb_decoders = [], []
         # like Keras, the layers exist (randomly initialised) until load_weights() is called
         self.set_weights(random_weights(cfg) if weights is None else weights)
 
@@ -121,10 +143,18 @@ class NeuralPUSCHReceiver:
         return {k: v for k, v in out.items() if not k.startswith("_")}
 
     def __call__(self, inputs: Tuple, no=None, mcs_arr_eval: Sequence[int] = (0,), mcs_ue_mask_eval=None):
-        """``NeuralPUSCHReceiver.forward`` inference branch: returns
-        ``(llr, h_hat_refined, h_hat, tb_crc_status=None)`` — see the module doc-string."""
+        """``NeuralPUSCHReceiver.forward`` inference branch: ``(b_hat, h_hat_refined, h_hat, tb_crc_status)`` with
+        transport-block decoding, ``(llr, h_hat_refined, h_hat, None)`` without — see the module doc-string."""
         out = self.llrs(inputs, mcs_arr_eval, mcs_ue_mask_eval)
-        return out["llr"], out["h_hat_refined"], out["h_hat"], None
+        if not self._tb_decoders:
+            return out["llr"], out["h_hat_refined"], out["h_hat"], None
+        b_hat, tb_crc_status = self._tb_decoders[int(mcs_arr_eval[0])](out["llr"])     # :1600
+        return b_hat, out["h_hat_refined"], out["h_hat"], tb_crc_status
+
+    @property
+    def tb_encoders(self):
+        """One ``tb.TBEncoder`` per supported MCS (empty without the base-graph tables)."""
+        return self._tb_encoders
 
     forward = __call__
 

@@ -72,12 +72,15 @@ def make_slots(cfg: NrxConfig, grid: Optional[PuschGrid] = None, batch: int = 1,
                delay_spread_ns: Sequence[float] = (100.0, 300.0),
                doppler_hz: Sequence[float] = (400.0, 100.0),
                per_ue_power_norm: bool = False,
-               sparse_paths: Optional[int] = None) -> SlotBatch:
+               sparse_paths: Optional[int] = None,
+               coded_bits: Optional[np.ndarray] = None) -> SlotBatch:
     """Generate ``batch`` slots.  ``mcs_per_ue[u]`` indexes ``cfg.mcs_index`` (default: head 0).
 
     ``sparse_paths`` switches to a ray-traced-shape channel (that many discrete paths with
     log-normal powers and uniform delays) for the site-specific configuration;
-    ``per_ue_power_norm`` mirrors ``channel_norm_eval = True``.
+    ``per_ue_power_norm`` mirrors ``channel_norm_eval = True``.  ``coded_bits`` [batch, U, n_data_res x bits] (the
+    output of a transport-block encoder, neural_rx_b200/tb.py) replaces the random payload; channel and noise
+    realisations of a seed do not depend on it.
     """
     grid = build_grid(cfg) if grid is None else grid
     U, F, T, N = grid.num_tx, grid.num_subcarriers, grid.num_ofdm_symbols, cfg.num_rx_antennas
@@ -107,6 +110,8 @@ def make_slots(cfg: NrxConfig, grid: Optional[PuschGrid] = None, batch: int = 1,
             x = np.zeros((T, F), np.complex128)
             nb = bits_ue[u]
             bb = rng.integers(0, 2, size=(n_data, nb), dtype=np.uint8)
+            if coded_bits is not None:
+                bb = np.asarray(coded_bits[b, u], np.uint8)[:n_data * nb].reshape(n_data, nb)
             const = qam_constellation(nb)
             idx = np.zeros(n_data, np.int64)
             for k in range(nb):
