@@ -243,7 +243,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots-per-pass", type=int, default=int(os.environ.get("NRX_SLOTS_PER_PASS", "0")))
-    ap.add_argument("--fused", type=int, default=int(os.environ.get("NRX_FUSED", "1")),
+    ap.add_argument("--fused", type=int, default=int(os.environ.get("NRX_FUSED", "6")),
                     help="execution plan of the sep-conv stacks (nrx_set_fused)")
     ap.add_argument("--host-chunk", type=int, default=int(os.environ.get("NRX_HOST_CHUNK", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -363,9 +363,9 @@ def main():
         # taken on the kernel sources that are running now (tools/ncu_summary.py stores their hash)
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
-        ncu_name = {"stack_update": "nrx_stack_ws_kernel<1>" if args.fused == 5 else "nrx_stack_kernel<1, 0>",
+        ncu_name = {"stack_update": "nrx_stack_ws_kernel<1>" if args.fused >= 5 else "nrx_stack_kernel<1, 0>",
                     "stack_init": "nrx_stack_ws_kernel<0>" if args.fused == 5 else "nrx_stack_kernel<0, 0>",
-                    "agg": "nrx_agg_kernel<2>", "readout": "nrx_readout_kernel"}.get(dom)
+                    "agg": "nrx_agg_ws_kernel", "readout": "nrx_readout_kernel"}.get(dom)
         if os.path.exists(tpath) and ncu_name and passes == 1:
             with open(tpath) as f:
                 tj = json.load(f)
@@ -466,7 +466,7 @@ def main():
         single = world == 1
         if single and not args.no_latency:
             # batch-1 latency uses plan 2 (message MLP fused into the stack kernels: 12 instead of 20
-            # launches for nrx_large); throughput above uses plan 1
+            # launches for nrx_large); throughput above uses the default plan
             lat = {}
             y1, a1 = ys[0][:1].contiguous(), act[:1].contiguous()
             eng.set_fused(2)

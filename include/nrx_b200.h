@@ -90,7 +90,7 @@ int nrx_get_num_it(const nrx_engine* e, int32_t* num_it);
 int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
 
 /* Execution plan of the sep-conv stacks (StateInit :61-132, UpdateState :210-270):
- *   fused == 1 (default): one kernel per stack, the two 128-channel hidden activations stay in
+ *   fused == 1:           one kernel per stack, the two 128-channel hidden activations stay in
  *                         shared memory (line-buffer fusion along the subcarrier axis); one
  *                         aggregation kernel per iteration (any number of users);
  *   fused == 2:           as 1, but with two users the message MLP of AggregateUserStates
@@ -100,13 +100,16 @@ int nrx_set_slots_per_pass(nrx_engine* e, int32_t slots);
  *   fused == 5:           as 1, but the stacks run in the warp-specialised, software-pipelined kernel
  *                         (nrx_stack_ws.cuh: depthwise warps, an MMA / TMA issuing warp and epilogue
  *                         warps work on two tiles concurrently; needs cuTensorMapEncodeTiled from
- *                         the driver).  Bit-identical to plan 1; 2 % faster per 30-slot UpdateState
- *                         launch on B200;
+ *                         the driver).  Bit-identical to plan 1; 3 % faster per 30-slot UpdateState
+ *                         launch on B200, 7 % slower per StateInit launch;
+ *   fused == 6 (default): StateInit in the serial kernel of plan 1, UpdateState in the pipelined kernel of
+ *                         plan 5 — each stack in the kernel that runs it fastest (plan 1 if the driver lacks
+ *                         cuTensorMapEncodeTiled);
  *   fused == 0:           one kernel per SeparableConv2D layer, activations through HBM/L2;
  *   fused == 3, 4:        two measured-slower experiments of round 1 (CTA-pair GEMMs, TMEM-resident
  *                         stack); only in builds with -DNRX_EXPERIMENTAL_PLANS, otherwise
  *                         NRX_ERR_UNSUPPORTED.
- * Plans 0, 1 and 5 are bit-identical; plan 2 differs at fp16 round-off. */
+ * Plans 0, 1, 5 and 6 are bit-identical; plan 2 differs at fp16 round-off. */
 int nrx_set_fused(nrx_engine* e, int32_t fused);
 
 /* Inactive-user skipping (off by default = the reference's behaviour: it computes all users and ignores the
@@ -231,7 +234,7 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches);
  *   nrx_debug_aggregate: a = AggregateUserStates_it(s, active_tx)
  *   nrx_debug_stack:     it >= 0: s_out = UpdateState_it(a, s) (residual included);
  *                        it <  0: s_out = StateInit_stack(z0), z0 rows of 32 channels [y | pe | h_ls | 0]
- *                        (execution plan 1 or 5 as set by nrx_set_fused)
+ *                        (execution plan 1, 5 or 6 as set by nrx_set_fused)
  *   nrx_debug_readout:   llr_grid [B][U][F][T][out_bits], h_hat_refined [B][U][F][T][2*N_rx] from s
  *   nrx_debug_option:    NRX_OPT_AGG_PIPELINED (default 1): 0 runs the one-tile-per-CTA aggregation kernel also for
  *                        two users (the pipelined kernel must reproduce it bit for bit);

@@ -111,7 +111,8 @@ struct nrx_engine {
     std::vector<uint8_t*> tm_blobs;                 // [it] its pointwise B images (output channels in fragment order)
 #endif
     int skip_inactive = 0;                          // nrx_set_skip_inactive: planes of inactive users are not computed
-    int fused = 1;                                  // 4: TMEM-resident UpdateState stacks (nrx_stack_tm.cuh);
+    int fused = 6;                                  // 6 (default): serial StateInit kernel + pipelined UpdateState kernels;
+                                                    // 5: both pipelined; 4: TMEM-resident UpdateState stacks (nrx_stack_tm.cuh);
                                                     // 1: fused stacks + aggregation kernel, 2: fused stacks with the message
                                                     // MLP in their tail (two users only), 3: CTA-pair stack kernels
                                                     // (experimental), 0: layer-per-kernel
@@ -347,8 +348,32 @@ TensorMapEncodeFn tensor_map_encoder() {
     return fn;
 }
 
+// A tensor map is a pure function of (address, shape, box, swizzle): the forwards of an engine encode the same dozen maps
+// over and over (workspace buffers, ping-pong states), so the encoded descriptors are kept in a small per-thread cache
+// instead of calling the driver for every launch.
+struct MapKey {
+    const void* base;
+    int planes, rows, ch, box_rows, swizzle;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && planes == o.planes && rows == o.rows && ch == o.ch && box_rows == o.box_rows && swizzle == o.swizzle;
+    }
+};
+bool cached_map(const MapKey& k, CUtensorMap* m, bool store) {
+    thread_local std::vector<std::pair<MapKey, CUtensorMap>> cache;
+    if (store) {
+        if (cache.size() >= 64) cache.clear();
+        cache.emplace_back(k, *m);
+        return true;
+    }
+    for (const auto& kv : cache)
+        if (kv.first == k) { *m = kv.second; return true; }
+    return false;
+}
+
 // [planes][rows][64] fp16 activation tensor, box = box_rows rows x 128 B, 128-byte swizzle
 int make_rows_map(CUtensorMap* m, const __half* base, int planes, int rows, int box_rows) {
+    const MapKey key{base, planes, rows, 64, box_rows, 1};
+    if (cached_map(key, m, false)) return NRX_OK;
     if (!tensor_map_encoder()) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled: driver entry point not found");
     const cuuint64_t dims[3] = {64, cuuint64_t(rows), cuuint64_t(planes)};
     const cuuint64_t strides[2] = {128, cuuint64_t(rows) * 128};
@@ -356,11 +381,15 @@ int make_rows_map(CUtensorMap* m, const __half* base, int planes, int rows, int 
     const CUresult r = tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    if (r != CUDA_SUCCESS) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    cached_map(key, m, true);
+    return NRX_OK;
 }
 // [planes][rows][ch] fp16 activation tensor, box = box_rows rows x ch channels, no swizzle: the layer-1 window of
 // the pipelined stack kernel (rows before / after the plane read zeros = the 'same' padding of the first layer)
 int make_window_map(CUtensorMap* m, const __half* base, int planes, int rows, int ch, int box_rows) {
+    const MapKey key{base, planes, rows, ch, box_rows, 0};
+    if (cached_map(key, m, false)) return NRX_OK;
     if (!tensor_map_encoder()) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled: driver entry point not found");
     const cuuint64_t dims[3] = {cuuint64_t(ch), cuuint64_t(rows), cuuint64_t(planes)};
     const cuuint64_t strides[2] = {cuuint64_t(ch) * 2, cuuint64_t(rows) * ch * 2};
@@ -368,7 +397,9 @@ int make_window_map(CUtensorMap* m, const __half* base, int planes, int rows, in
     const CUresult r = tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? NRX_OK : fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    if (r != CUDA_SUCCESS) return fail(NRX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+    cached_map(key, m, true);
+    return NRX_OK;
 }
 // box = one subcarrier (14 rows) of a (slot, user) plane
 int make_plane_map(CUtensorMap* m, const __half* base, int planes, int F) { return make_rows_map(m, base, planes, F * kT, kT); }
@@ -432,12 +463,15 @@ int launch_stack_ws(nrx_engine* e, cudaStream_t st, StackParams kp, int planes, 
         if (!rc) rc = make_window_map(&wp.map_s, kp.s_in, planes, F * kT, 64, kWsWin * kT);
     }
     if (rc) return rc;
-    kp.n_chunks = ws_choose_chunks(planes, F, e->num_sms);
-    kp.num_items = kp.n_chunks * planes;
+    int grid = set_stack_work(e, kp, planes, F);
+    if (!e->stack_balanced) {
+        kp.n_chunks = ws_choose_chunks(planes, F, e->num_sms);
+        kp.num_items = kp.n_chunks * planes;
+        grid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
+    }
     kp.sp_out = nullptr;
     kp.pair_agg = 0;
     wp.p = kp;
-    const int grid = kp.num_items < e->num_sms ? kp.num_items : e->num_sms;
     Timed t(e, st, MODE == kStackInit ? NRX_K_STACK_INIT : NRX_K_STACK_UPD);
     nrx_stack_ws_kernel<MODE><<<grid, kWsThreads, WsSmem<MODE>::kTotal, st>>>(wp);
     return NRX_OK;
@@ -545,6 +579,7 @@ int nrx_create(const nrx_model_desc* desc, const float* const* weight_arrays, co
 
     NRX_CUDA(cudaSetDevice(device));
     nrx_engine* e = new nrx_engine();
+    if (!tensor_map_encoder()) e->fused = 1;            // the pipelined kernels are fed by tensor-map TMA
     e->d = d;
     e->device = device;
     e->num_it = d.num_it;
@@ -854,12 +889,12 @@ int nrx_get_profile(nrx_engine* e, double* ms, int64_t* launches) {
 
 int nrx_set_fused(nrx_engine* e, int32_t fused) {
     if (!e) return fail(NRX_ERR_INVALID, "null engine");
-    if (fused < 0 || fused > 5) return fail(NRX_ERR_INVALID, "fused must be 0 ... 5");
+    if (fused < 0 || fused > 6) return fail(NRX_ERR_INVALID, "fused must be 0 ... 6");
 #ifndef NRX_EXPERIMENTAL_PLANS
     if (fused == 3 || fused == 4)
         return fail(NRX_ERR_UNSUPPORTED, "plans 3 and 4 are experiments that are not in the default build (-DNRX_EXPERIMENTAL_PLANS)");
 #endif
-    if (fused >= 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plan 4 needs cuTensorMapEncodeTiled (driver entry point not found)");
+    if (fused >= 4 && !tensor_map_encoder()) return fail(NRX_ERR_CUDA, "plans 4, 5 and 6 need cuTensorMapEncodeTiled (driver entry point not found)");
     e->fused = fused;
     return NRX_OK;
 }
@@ -899,7 +934,7 @@ int nrx_launches_per_forward(const nrx_engine* e, int32_t batch, int32_t* launch
     if (!e || !launches || batch < 1) return fail(NRX_ERR_INVALID, "nrx_launches_per_forward: bad argument");
     const int bp = pass_slots(e, batch);
     const int passes = (batch + bp - 1) / bp;
-    *launches = e->fused ? 1 + passes * ((e->skip_inactive && (e->fused == 1 || e->fused == 5) ? 1 : 0) + 1 + 1 + e->num_it * (e->d.max_num_tx == 2 && e->fused == 2 ? 1 : 2) + 1)
+    *launches = e->fused ? 1 + passes * ((e->skip_inactive && (e->fused == 1 || e->fused >= 5) ? 1 : 0) + 1 + 1 + e->num_it * (e->d.max_num_tx == 2 && e->fused == 2 ? 1 : 2) + 1)
                          : 1 + passes * (1 + 3 + e->num_it * 4 + 1);
     return NRX_OK;
 }
@@ -1043,8 +1078,8 @@ int forward_impl(nrx_engine* e, void* cuda_stream, int32_t batch, const AerialIn
             kp.active_tx = active_tx + size_t(b0) * U;
             kp.pair_agg = 0;
             kp.sp_out = pair ? sp_cur : nullptr;
-            const bool piped = e->fused == 5;           // plan 5: warp-specialised pipelined stack kernels
-            if (piped && !io_index) {                   // (per-user StateInit stacks, Var-IO: the serial kernel switches weights per item)
+            const bool piped = e->fused >= 5;           // plans 5, 6: warp-specialised pipelined UpdateState kernels
+            if (e->fused == 5 && !io_index) {           // plan 5 also runs StateInit there (measured slower: 431 vs 401 us)                   // (per-user StateInit stacks, Var-IO: the serial kernel switches weights per item)
                 if (const int rc = launch_stack_ws<kStackInit>(e, st, kp, BU, F, e->init_bias[llr_head].v)) return rc;
             } else {
                 Timed t(e, st, NRX_K_STACK_INIT);
@@ -1415,7 +1450,7 @@ int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack,
         return fail(NRX_ERR_INVALID, "nrx_debug_stack: bad argument");
     const bool init = it < 0;
     if (init ? !z0_f16 : (!a_f16 || !s_f16)) return fail(NRX_ERR_INVALID, "nrx_debug_stack: null input");
-    if (e->fused != 1 && e->fused != 5) return fail(NRX_ERR_INVALID, "nrx_debug_stack: plans 1 and 5 only");
+    if (e->fused != 1 && e->fused < 5) return fail(NRX_ERR_INVALID, "nrx_debug_stack: plans 1, 5 and 6 only");
     NRX_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const nrx_model_desc& d = e->d;
@@ -1431,7 +1466,7 @@ int nrx_debug_stack(nrx_engine* e, void* cuda_stream, int32_t it, int32_t stack,
     kp.wblob = init ? e->stack_init_blob : e->stack_upd_blobs[it];
     kp.default_stack = init ? stack : 0;
     kp.n_stacks = init ? d.n_io : 1;
-    if (e->fused == 5) {
+    if (e->fused == 5 || (e->fused == 6 && !init)) {
         const int rc = init ? launch_stack_ws<kStackInit>(e, st, kp, BU, F, e->init_bias[stack].v)
                             : launch_stack_ws<kStackUpdate>(e, st, kp, BU, F, e->upd_bias[it].v);
         if (rc) return rc;

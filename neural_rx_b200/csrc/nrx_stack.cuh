@@ -50,7 +50,7 @@ struct StackParams {
     const int32_t* stack_index;  // [BU] or null
     const float* pos_enc;        // [U][F][T][2]   (init)
     int F, U, d_s;
-    int n_chunks, num_items;     // n_chunks == 0: balanced ranges (nrx_stack_kernel only), see stack_begin
+    int n_chunks, num_items;     // n_chunks == 0: balanced ranges (nrx_stack_kernel, nrx_stack_ws_kernel), see stack_begin
     int num_planes;              // planes of the launch (all of them; with plane_list the active count is plane_list[0])
     int default_stack;
     int n_stacks;                // stacks in wblob: stack_index values are clamped to [0, n_stacks)
@@ -67,7 +67,7 @@ __device__ __forceinline__ int stack_plane(const StackParams& p, int item, int& 
     return p.plane_list ? p.plane_list[1 + pl] : pl;
 }
 
-// Work distribution of nrx_stack_kernel.  n_chunks > 0: every plane is cut into n_chunks equal chunks, CTA b takes the
+// Work distribution of nrx_stack_kernel / nrx_stack_ws_kernel.  n_chunks > 0: every plane is cut into n_chunks equal chunks, CTA b takes the
 // items b, b + grid, ... (choose_chunks picks n_chunks; the makespan is waves x steps of the longest chunk).
 // n_chunks == 0 ("balanced"): the launch's planes are laid end to end (W = planes x F subcarriers) and CTA b owns the
 // subcarriers [b W / G, (b + 1) W / G) of that line, G = min(grid, W / kMinSeg); where the range crosses a plane boundary

@@ -243,11 +243,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) nrx_stack_ws_kernel(const __gri
     uint32_t n_dfull[2] = {0, 0};                       // P: completed phases of the two "accumulator full" mbarriers
     int loaded_stack = -1;
 
-    const int num_items = stack_num_items(p);
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int cj;
-        const int bu = stack_plane(p, item, cj);
-        const int c0 = int((long long)cj * p.F / p.n_chunks), c1 = int((long long)(cj + 1) * p.F / p.n_chunks);
+    StackCursor cur = stack_begin(p);                   // balanced CTA ranges or equal chunks per plane (nrx_stack.cuh)
+    int bu, c0, c1;
+    while (stack_next(p, cur, bu, c0, c1)) {
         const int K = (c1 - c0 + kWsRunIn + kWsStepF - 1) / kWsStepF;
         const int stack = stack_of(p, bu);
         __syncthreads();                                // B1: every role has finished the previous item

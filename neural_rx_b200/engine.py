@@ -203,9 +203,10 @@ class NrxEngine:
         self._ws = None
 
     def set_fused(self, fused) -> None:
-        """1/True: fused stack kernels + aggregation kernel (default); 2: fused stacks with the
-        message MLP in their tail (two users); 5: warp-specialised pipelined stack kernels; 0/False: one kernel
-        per SeparableConv2D layer (3, 4: round-1 experiments, only in -DNRX_EXPERIMENTAL_PLANS builds)."""
+        """6 (default): serial StateInit kernel + pipelined UpdateState kernels; 1/True: serial fused stack kernels +
+        aggregation kernel; 2: fused stacks with the message MLP in their tail (two users); 5: warp-specialised
+        pipelined kernels for both stacks; 0/False: one kernel per SeparableConv2D layer (3, 4: round-1 experiments,
+        only in -DNRX_EXPERIMENTAL_PLANS builds)."""
         self._check(self._lib.nrx_set_fused(self._h, int(fused)))
 
     def set_skip_inactive(self, enable: bool) -> None:

@@ -40,10 +40,12 @@ def _emul_tol(label):
 TOL_EMUL = 4e-3        # vs the oracle with the engine's rounding points emulated
 
 
-def _engine(cfg, weights, grid, fused=True):
+def _engine(cfg, weights, grid, fused=None):
+    """fused = None: the engine's default execution plan (6)."""
     from neural_rx_b200.engine import NrxEngine
     eng = NrxEngine(cfg, weights, grid, device=0)
-    eng.set_fused(fused)
+    if fused is not None:
+        eng.set_fused(fused)
     return eng
 
 
@@ -120,7 +122,7 @@ def test_fused_equals_layerwise(label, n_prb, batch):
     if cfg.num_mcss_supported > 1:
         kw = dict(io_index=np.tile(np.array([[0, 1]], np.int32), (batch, 1)))
     outs = []
-    for fused in (1, 2, 0, 5):
+    for fused in (1, 2, 0, 5, 6):
         eng = _engine(cfg, weights, grid, fused=fused)
         outs.append(_run(eng, sb, **dict(kw)))
         eng.close()
@@ -129,6 +131,7 @@ def test_fused_equals_layerwise(label, n_prb, batch):
         # plan 5 (warp-specialised pipelined stacks, nrx_stack_ws.cuh): other tiling (8-subcarrier steps, ring
         # buffers), other thread mapping, other schedule - the same sums in the same order: bit-identical
         assert np.array_equal(outs[3][k], outs[0][k]), k
+        assert np.array_equal(outs[4][k], outs[0][k]), k      # plan 6 (default): serial StateInit + pipelined UpdateState
         # the two-user fast path takes the other user's message directly instead of forming
         # (sp_0 + sp_1) - sp_u in fp32 (utils/neural_rx.py:196) and rounds sp (not a) to fp16:
         # same function, differences at fp16 round-off level
@@ -262,7 +265,8 @@ def test_inactive_user_skipping(num_tx, active, fused):
     ("nrx_rt", 273, [[1, 1]]),
 ])
 @pytest.mark.parametrize("skip", [0, 1])
-def test_balanced_stack_ranges_equal_uniform_chunks(label, n_prb, active, skip):
+@pytest.mark.parametrize("plan", [1, 5])
+def test_balanced_stack_ranges_equal_uniform_chunks(label, n_prb, active, skip, plan):
     """Default work distribution of the fused stack kernels (balanced CTA ranges over the planes laid end to end,
     nrx_plan_stack_range; with inactive-user skipping over the ACTIVE planes only, counted on the device) against
     equal chunks per plane (NRX_OPT_STACK_BALANCED = 0): every output bit for bit — an item's run-in recomputes the
@@ -272,7 +276,7 @@ def test_balanced_stack_ranges_equal_uniform_chunks(label, n_prb, active, skip):
     grid = build_grid(cfg, n_size_bwp=n_prb)
     act = np.asarray(active, np.float32)
     sb = make_slots(cfg, grid, batch=act.shape[0], ebno_db=7.0, seed=29, active=act)
-    eng = _engine(cfg, weights, grid, fused=1)
+    eng = _engine(cfg, weights, grid, fused=plan)
     eng.set_skip_inactive(bool(skip))
     bal = _run(eng, sb)
     eng.debug_option(eng.OPT_STACK_BALANCED, 0)

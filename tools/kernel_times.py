@@ -12,9 +12,12 @@ y = torch.as_tensor(np.repeat(sb.y, 30, axis=0)).cuda(); act = torch.ones((30, 2
 eng = E.NrxEngine(cfg, w, grid)
 for _ in range(3): eng.forward(y, act, want=("llr",))
 torch.cuda.synchronize(); eng.set_profiling(True); eng.get_profile()
-for balanced in (1, 0):
-    eng.debug_option(eng.OPT_STACK_BALANCED, balanced)
-    for want in (("llr", "h_hat_refined"), ("llr", "h_hat_refined", "h_hat")):
-        for _ in range(10): eng.forward(y, act, want=want)
+for plan in (1, 5):
+    eng.set_fused(plan)
+    for balanced in (1, 0):
+        eng.debug_option(eng.OPT_STACK_BALANCED, balanced)
+        for _ in range(3): eng.forward(y, act, want=("llr", "h_hat_refined"))
+        torch.cuda.synchronize(); eng.get_profile()
+        for _ in range(10): eng.forward(y, act, want=("llr", "h_hat_refined"))
         torch.cuda.synchronize(); pr = eng.get_profile()
-        print("balanced" if balanced else "uniform", want, {k: round(v["ms"] / max(v["launches"], 1) * 1e3, 1) for k, v in pr.items() if v["launches"]})
+        print("plan", plan, "balanced" if balanced else "uniform ", {k: round(v["ms"] / max(v["launches"], 1) * 1e3, 1) for k, v in pr.items() if v["launches"]})
