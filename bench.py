@@ -362,7 +362,7 @@ def main():
         # DRAM bytes per launch of that kernel from this round's committed `ncu --set full` capture — only if it was
         # taken on the kernel sources that are running now (tools/ncu_summary.py stores their hash)
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02b_traffic.json")
         ncu_name = {"stack_update": "nrx_stack_ws_kernel<1>" if args.fused >= 5 else "nrx_stack_kernel<1, 0>",
                     "stack_init": "nrx_stack_ws_kernel<0>" if args.fused == 5 else "nrx_stack_kernel<0, 0>",
                     "agg": "nrx_agg_ws_kernel", "readout": "nrx_readout_kernel"}.get(dom)
@@ -371,9 +371,9 @@ def main():
                 tj = json.load(f)
             if tj.get("source_hash") == source_hash():
                 traffic = tj.get("kernels", {}).get(ncu_name, {}).get("dram_bytes_per_launch")
-                traffic_src = f"profiles/r02_traffic.json (ncu --set full, source hash {tj.get('source_hash')})"
+                traffic_src = f"profiles/r02b_traffic.json (ncu --set full, source hash {tj.get('source_hash')})"
             else:
-                traffic_src = "omitted: profiles/r02_traffic.json was captured on other kernel sources"
+                traffic_src = "omitted: profiles/r02b_traffic.json was captured on other kernel sources"
         roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "frac_of_burst_peak": achieved / peak_burst,
                 "frac_of_sustained_peak": achieved / peak_sust,

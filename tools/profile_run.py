@@ -19,7 +19,8 @@ sb = make_slots(cfg, grid, batch=1, ebno_db=4.0, seed=1)
 y = torch.as_tensor(np.repeat(sb.y, batch, axis=0)).cuda()
 act = torch.ones((batch, 2), device="cuda")
 eng = NrxEngine(cfg, w, grid)
-eng.set_fused(int(os.environ.get("NRX_FUSED", "1")))
+if "NRX_FUSED" in os.environ:
+    eng.set_fused(int(os.environ["NRX_FUSED"]))        # default: the engine's default plan (6)
 for _ in range(iters):
     out = eng.forward(y, act, want=("llr", "h_hat_refined"))
 torch.cuda.synchronize()
