@@ -61,3 +61,56 @@ def test_counters_world_size_2():
     for _, tot, mx in res:
         assert tot == want and tot["slots"] == 9
         assert mx == 2.0
+
+
+# ---- BLER harness (neural_rx_b200/bler.py): the counters of an Eb/N0 point do not depend on the number of ranks ----
+def _bler_setup():
+    from neural_rx_b200 import tb as TB
+    from neural_rx_b200.config import get_config
+    from neural_rx_b200.pusch import build_grid
+    from oracle import nrx_oracle as O
+    from tests.common import get_weights, oracle_arch, oracle_net
+    cfg = get_config("nrx_rt")
+    grid = build_grid(cfg, n_size_bwp=4)
+    weights, _ = get_weights(cfg)
+    enc = TB.pusch_tb_encoder(cfg, grid, base_graph="standin")
+    dec = TB.TBDecoder(enc, num_bp_iter=8)
+    net, arch = oracle_net(cfg, weights), oracle_arch(cfg)
+
+    def llr_fn(y, act):                                    # the CPU oracle stands in for the CUDA receiver
+        return np.asarray(O.receiver_forward(net, arch, y, grid.pilots, grid.pilot_mask, act)["llr"], np.float32)
+    return cfg, grid, enc, dec, llr_fn
+
+
+def _bler_worker(rank, world, port, q):
+    from neural_rx_b200.bler import sim_point
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, grid, enc, dec, llr_fn = _bler_setup()
+    tot, _ = sim_point(llr_fn, cfg, grid, enc, dec, point=1, ebno_db=3.0, num_slots=7, batch=2, rank=rank, world=world)
+    q.put((rank, tot))
+    dist.destroy_process_group()
+
+
+def test_bler_point_counters_do_not_depend_on_world_size():
+    from neural_rx_b200.bler import sim_point
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cfg, grid, enc, dec, llr_fn = _bler_setup()
+    want, first = sim_point(llr_fn, cfg, grid, enc, dec, point=1, ebno_db=3.0, num_slots=7, batch=3, keep_first=2)
+    assert want["blocks"] == 14 and want["bits"] == 14 * enc.tb_size and len(first) == 2
+    assert 0 <= want["block_errors"] <= 14
+    for _, tot in res:
+        assert tot == want

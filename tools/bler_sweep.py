@@ -29,24 +29,9 @@ sys.path.insert(0, ROOT)
 
 from neural_rx_b200 import tb as TB  # noqa: E402
 from neural_rx_b200.config import get_config  # noqa: E402
-from neural_rx_b200.distributed import slot_shard, sum_counters  # noqa: E402
+from neural_rx_b200.bler import sim_point  # noqa: E402
 from neural_rx_b200.pusch import build_grid  # noqa: E402
-from neural_rx_b200.synth import make_slots  # noqa: E402
 from neural_rx_b200.weights import load_weights, random_weights  # noqa: E402
-
-
-def coded_slots(cfg, grid, enc, idx, point, ebno):
-    """Slots `idx` of SNR point `point`: TB bits (seeded), coded bits on the grid, channel + noise."""
-    U = grid.num_tx
-    tbs, ys, acts = [], [], []
-    for i in idx:
-        rng = np.random.default_rng([77, point, i])
-        b = rng.integers(0, 2, (1, U, enc.tb_size), dtype=np.uint8)
-        sb = make_slots(cfg, grid, batch=1, ebno_db=float(ebno), seed=1000 * point + i, coded_bits=enc(b))
-        tbs.append(b)
-        ys.append(sb.y)
-        acts.append(sb.active_tx)
-    return np.concatenate(tbs), np.concatenate(ys), np.concatenate(acts)
 
 
 def main():
@@ -89,30 +74,13 @@ def main():
                  if enc.base_graph_source != "3gpp" else ""))
         print("# ebno_db  bit_errors        bits        BER  block_errors  blocks       BLER   seconds" +
               ("   oracle_block_errors  engine_block_errors  (same slots)  decisions_differ" if args.check_oracle else ""))
+    def llr_fn(y, act):
+        return rx.llrs((torch.as_tensor(y).cuda(), torch.as_tensor(act).cuda()), want=("llr",))["llr"]
+
     for pi, ebno in enumerate(points):
-        s_lo, s_hi = slot_shard(args.slots, rank, world)
         t0 = time.perf_counter()
-        c = {"bit_errors": 0, "bits": 0, "block_errors": 0, "blocks": 0}
-        first = []
-        n_iter = -(-(-(-args.slots // world)) // args.batch)           # the same on every rank: the early-stop test is a collective
-        for it in range(n_iter):
-            idx = range(min(s_lo + it * args.batch, s_hi), min(s_lo + (it + 1) * args.batch, s_hi))
-            if len(idx):
-                tb_bits, y, act = coded_slots(cfg, grid, enc, idx, pi, ebno)
-                llr = rx.llrs((torch.as_tensor(y).cuda(), torch.as_tensor(act).cuda()), want=("llr",))["llr"]
-                b_hat, ok = dec(llr)                                    # on the GPU
-                b_hat, ok = b_hat.cpu().numpy(), ok.cpu().numpy()
-                on = act > 0
-                c["bit_errors"] += int(((b_hat != tb_bits) & on[..., None]).sum())
-                c["bits"] += int(on.sum()) * enc.tb_size
-                c["block_errors"] += int((~ok & on).sum())
-                c["blocks"] += int(on.sum())
-                if rank == 0 and len(first) < args.check_oracle:
-                    k = args.check_oracle - len(first)
-                    first += list(zip(y[:k], act[:k], ok[:k], b_hat[:k]))
-            if sum_counters(dict(c))["block_errors"] >= args.target_block_errors:
-                break
-        tot = sum_counters(c)
+        tot, first = sim_point(llr_fn, cfg, grid, enc, dec, pi, float(ebno), args.slots, args.batch, rank, world,
+                               args.target_block_errors, args.check_oracle)
         if rank == 0:
             dt = time.perf_counter() - t0
             line = (f"{ebno:8.2f} {tot['bit_errors']:11d} {tot['bits']:11d} {tot['bit_errors'] / max(tot['bits'], 1):10.3e} "
