@@ -61,8 +61,9 @@ class NeuralPUSCHReceiver:
                     enc = _tb.pusch_tb_encoder(cfg, self._grid, i, rn, ni, "3gpp" if tb_decoding == "auto" else tb_decoding)
                     self._tb_encoders.append(enc)
                     self._tb_decoders.append(_tb.TBDecoder(enc, num_bp_iter=num_bp_iter, cn_type=cn_type))
-            except _tb.BaseGraphUnavailable:
-                if tb_decoding == "3gpp":
+            except (_tb.BaseGraphUnavailable, ValueError):
+                # "auto": no tables in this installation (or a grid the TB chain has no size for): LLRs are returned
+                if tb_decoding != "auto":
                     raise
                 self._tb_encoders, self._tb_decoders = [], []
         # like Keras, the layers exist (randomly initialised) until load_weights() is called
