@@ -170,3 +170,41 @@ def test_pusch_tb_encoder_of_the_configs(label, n_prb):
     assert grid.num_data_res == n_prb * 144
     assert enc.bg == 1 or enc.tb_size <= 3824
     assert abs(enc.tb_size / enc.num_coded_bits - enc.coderate) < 0.02
+
+
+@pytest.mark.parametrize("n_prb,qm,rate,bg,num_cbs", [
+    (100, 2, 0.2, 2, 2),        # rate <= 0.25: BG2 although the block is long (K_cb = 3840), two code blocks
+    (273, 2, 0.12, 2, 3),       # repetition: E_r = 26 208 > N_cb = 16 000
+    (35, 4, 0.3, 1, 1),         # one BG1 block with fillers (K' = 6 040, K = 6 336)
+    (66, 6, 0.55, 1, 4),
+    (51, 6, 0.9, 1, 5),         # heavy puncturing, unequal E_r (8 808 / 8 814)
+])
+def test_segmentation_and_rate_matching_regimes(n_prb, qm, rate, bg, num_cbs):
+    """Every branch of TS 38.212 §6.2.2-6.2.5 the PUSCH configs can reach, on sizes from the TBS rule: base-graph
+    choice, multi-block segmentation with per-block CRC, fillers, repetition and puncturing, unequal E_r; the
+    noiseless round trip returns the bits and a passed CRC."""
+    tbs = TB.tb_size(n_prb, 144, qm, rate)
+    G = n_prb * 144 * qm
+    enc = TB.TBEncoder(tbs, G, rate, qm, base_graph="standin")
+    assert (enc.bg, enc.num_cbs) == (bg, num_cbs)
+    assert enc.k == (22 if bg == 1 else 10) * enc.z and enc.k_prime <= enc.k and enc.n_cb == (66 if bg == 1 else 50) * enc.z
+    assert sum(enc.cb_e) == G and all(e % qm == 0 for e in enc.cb_e) and max(enc.cb_e) - min(enc.cb_e) in (0, qm)
+    bits = np.random.default_rng(n_prb).integers(0, 2, (2, tbs), dtype=np.uint8)
+    coded = enc(bits)
+    b_hat, ok = TB.TBDecoder(enc)(6.0 * (2.0 * coded - 1.0).astype(np.float32))
+    assert ok.all() and np.array_equal(b_hat, bits)
+    flipped = coded.copy()
+    flipped[0, : G // 3] ^= 1                                   # a third of block 0 wrong: the TB CRC must fail
+    _, ok = TB.TBDecoder(enc, num_bp_iter=4)(6.0 * (2.0 * flipped - 1.0).astype(np.float32))
+    assert not ok[0] and ok[1]
+
+
+@pytest.mark.parametrize("tbs,G,qm,rate,kb_cols", [(24, 120, 2, 0.2, 6), (504, 1200, 2, 0.42, 8), (608, 1400, 4, 0.43, 9), (3824, 8000, 4, 0.48, 10)])
+def test_short_blocks_on_bg2(tbs, G, qm, rate, kb_cols):
+    """BG2 with K_b = 6 / 8 / 9 / 10 systematic columns in use (TS 38.212 §5.2.2): the unused columns are fillers."""
+    enc = TB.TBEncoder(tbs, G, rate, qm, base_graph="standin")
+    assert enc.bg == 2 and enc.tb_crc == "16" and enc.num_cbs == 1
+    assert enc.z == TB.select_lifting(kb_cols, enc.k_prime)[0] and enc.k == 10 * enc.z
+    bits = np.random.default_rng(tbs).integers(0, 2, (3, tbs), dtype=np.uint8)
+    b_hat, ok = TB.TBDecoder(enc)(5.0 * (2.0 * enc(bits) - 1.0).astype(np.float32))
+    assert ok.all() and np.array_equal(b_hat, bits)
