@@ -46,7 +46,7 @@ typedef struct nrx_engine nrx_engine;
 typedef struct nrx_model_desc {
     int32_t num_rx_ant;          /* N_rx in [1, 7]                                                  */
     int32_t max_num_tx;          /* U in [1, NRX_MAX_TX]                                            */
-    int32_t num_subcarriers;     /* F = 12 * n_size_bwp: a positive multiple of focc_block          */
+    int32_t num_subcarriers;     /* F = 12 * n_size_bwp: a positive multiple of focc_block, < 65536  */
     int32_t num_ofdm_symbols;    /* T: must be 14                                                   */
     int32_t d_s;                 /* state width: a multiple of 4 in [4, 60] (56 in all shipped configs; two
                                     more channels of the 64-wide state rows carry the positional encoding)  */
