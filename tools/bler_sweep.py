@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--base-graph", default="auto", choices=("auto", "3gpp", "standin"))
     ap.add_argument("--target-block-errors", type=int, default=500)
     ap.add_argument("--check-oracle", type=int, default=0)
+    ap.add_argument("--num-it", type=int, nargs="+", default=None,
+                    help="CGNN iterations to evaluate (num_it sweep of results/nrx_large_sweep_results); default: the cfg's")
     args = ap.parse_args()
 
     import torch
@@ -77,27 +79,35 @@ def main():
     def llr_fn(y, act):
         return rx.llrs((torch.as_tensor(y).cuda(), torch.as_tensor(act).cuda()), want=("llr",))["llr"]
 
-    for pi, ebno in enumerate(points):
+    def run_point(pi, ebno):
         t0 = time.perf_counter()
         tot, first = sim_point(llr_fn, cfg, grid, enc, dec, pi, float(ebno), args.slots, args.batch, rank, world,
                                args.target_block_errors, args.check_oracle)
-        if rank == 0:
-            dt = time.perf_counter() - t0
-            line = (f"{ebno:8.2f} {tot['bit_errors']:11d} {tot['bits']:11d} {tot['bit_errors'] / max(tot['bits'], 1):10.3e} "
-                    f"{tot['block_errors']:13d} {tot['blocks']:7d} {tot['block_errors'] / max(tot['blocks'], 1):10.3e} {dt:9.1f}")
-            if first:
-                from oracle import nrx_oracle as O
-                from tests.common import oracle_arch, oracle_net
-                net, arch = oracle_net(cfg, weights), oracle_arch(cfg)
-                e_o = e_g = diff = 0
-                for ys, a, ok_g, bh_g in first:
-                    ref = O.receiver_forward(net, arch, ys[None], grid.pilots, grid.pilot_mask, a[None])["llr"]
-                    bh_o, ok_o = dec(np.asarray(ref, np.float32))
-                    e_o += int((~ok_o[0] & (a > 0)).sum())
-                    e_g += int((~ok_g & (a > 0)).sum())
-                    diff += int(((ok_o[0] != ok_g) & (a > 0)).sum())
-                line += f"   {e_o:19d}  {e_g:19d}  {len(first) * U:12d}  {diff:16d}"
-            print(line, flush=True)
+        if rank != 0:
+            return
+        dt = time.perf_counter() - t0
+        line = (f"{ebno:8.2f} {tot['bit_errors']:11d} {tot['bits']:11d} {tot['bit_errors'] / max(tot['bits'], 1):10.3e} "
+                f"{tot['block_errors']:13d} {tot['blocks']:7d} {tot['block_errors'] / max(tot['blocks'], 1):10.3e} {dt:9.1f}")
+        if first:                                       # test aid: the same slots through the CPU oracle (test infrastructure)
+            from oracle import nrx_oracle as O
+            from tests.common import oracle_arch, oracle_net
+            net, arch = oracle_net(cfg, weights), oracle_arch(cfg)
+            e_o = e_g = diff = 0
+            for ys, a, ok_g, bh_g in first:
+                ref = O.receiver_forward(net, arch, ys[None], grid.pilots, grid.pilot_mask, a[None], num_it=rx.num_it)["llr"]
+                bh_o, ok_o = dec(np.asarray(ref, np.float32))
+                e_o += int((~ok_o[0] & (a > 0)).sum())
+                e_g += int((~ok_g & (a > 0)).sum())
+                diff += int(((ok_o[0] != ok_g) & (a > 0)).sum())
+            line += f"   {e_o:19d}  {e_g:19d}  {len(first) * U:12d}  {diff:16d}"
+        print(line, flush=True)
+
+    for num_it in (args.num_it or [rx.num_it]):
+        rx.num_it = num_it                              # utils/neural_rx.py:537-542: iterations can be dropped after training
+        if rank == 0 and args.num_it:
+            print(f"# num_it = {num_it}")
+        for pi, ebno in enumerate(points):
+            run_point(pi, ebno)
     if world > 1:
         dist.destroy_process_group()
 
