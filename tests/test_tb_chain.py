@@ -208,3 +208,16 @@ def test_short_blocks_on_bg2(tbs, G, qm, rate, kb_cols):
     bits = np.random.default_rng(tbs).integers(0, 2, (3, tbs), dtype=np.uint8)
     b_hat, ok = TB.TBDecoder(enc)(5.0 * (2.0 * enc(bits) - 1.0).astype(np.float32))
     assert ok.all() and np.array_equal(b_hat, bits)
+
+
+def test_tb_size_matches_the_reference_notebook_printout():
+    """The one transport-block size the reference tree shows: `model._transmitters[0].show()` in
+    notebooks/jumpstart_tutorial.ipynb (nrx_rt training grid: 4 PRB, MCS 14, mcs_table 1) prints num_res_per_prb : 144,
+    num_coded_bits : 2304, target_coderate : 0.5400390625, tb_size : 1256, n_rnti : 1, n_id : 1."""
+    cfg = get_config("nrx_rt")
+    grid = build_grid(cfg, n_size_bwp=4)
+    enc = TB.pusch_tb_encoder(cfg, grid, base_graph="standin")
+    assert grid.num_data_res // 4 == 144
+    assert enc.num_coded_bits == 2304 and enc.coderate == 0.5400390625 and enc.tb_size == 1256
+    assert TB.tb_size(4, 144, 4, 0.5400390625) == 1256
+    assert np.array_equal(enc.scramble_seq[0], TB.gold_sequence((1 << 15) + 1, 2304))
