@@ -15,14 +15,17 @@ from .distributed import slot_shard, sum_counters
 from .synth import make_slots
 
 
-def coded_slots(cfg, grid, enc, idx, point: int, ebno_db: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Slots ``idx`` of SNR point ``point``: seeded TB bits [n, U, tb_size], received grids y, activity flags."""
+def coded_slots(cfg, grid, enc, idx, point: int, ebno_db: float, active=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Slots ``idx`` of SNR point ``point``: seeded TB bits [n, U, tb_size], received grids y, activity flags
+    (``active`` [U] 0/1: the transmitters that are on in every slot, e.g. [1, 0] for the single-UE results of
+    ``results/nrx_rt_results``; default all)."""
     U = grid.num_tx
+    act1 = None if active is None else np.asarray(active, np.float32).reshape(1, U)
     tbs, ys, acts = [], [], []
     for i in idx:
         rng = np.random.default_rng([77, point, i])
         b = rng.integers(0, 2, (1, U, enc.tb_size), dtype=np.uint8)
-        sb = make_slots(cfg, grid, batch=1, ebno_db=float(ebno_db), seed=1000 * point + i, coded_bits=enc(b))
+        sb = make_slots(cfg, grid, batch=1, ebno_db=float(ebno_db), seed=1000 * point + i, coded_bits=enc(b), active=act1)
         tbs.append(b)
         ys.append(sb.y)
         acts.append(sb.active_tx)
@@ -30,7 +33,7 @@ def coded_slots(cfg, grid, enc, idx, point: int, ebno_db: float) -> Tuple[np.nda
 
 
 def sim_point(llr_fn: Callable, cfg, grid, enc, dec, point: int, ebno_db: float, num_slots: int, batch: int = 30,
-              rank: int = 0, world: int = 1, target_block_errors: int = 500, keep_first: int = 0
+              rank: int = 0, world: int = 1, target_block_errors: int = 500, keep_first: int = 0, active=None
               ) -> Tuple[Dict[str, int], List[tuple]]:
     """One Eb/N0 point.  ``llr_fn(y, active_tx) -> llr [n, U, num_coded_bits]`` (NumPy or torch; the decoder runs where
     the LLRs live).  Returns the job-wide counters and, on rank 0, the first ``keep_first`` (y, active, crc_ok, b_hat)
@@ -42,7 +45,7 @@ def sim_point(llr_fn: Callable, cfg, grid, enc, dec, point: int, ebno_db: float,
     for it in range(n_iter):
         idx = range(min(s_lo + it * batch, s_hi), min(s_lo + (it + 1) * batch, s_hi))
         if len(idx):
-            tb_bits, y, act = coded_slots(cfg, grid, enc, idx, point, ebno_db)
+            tb_bits, y, act = coded_slots(cfg, grid, enc, idx, point, ebno_db, active)
             b_hat, ok = dec(llr_fn(y, act))
             if hasattr(b_hat, "cpu"):
                 b_hat, ok = b_hat.cpu().numpy(), ok.cpu().numpy()

@@ -114,3 +114,12 @@ def test_bler_point_counters_do_not_depend_on_world_size():
     assert 0 <= want["block_errors"] <= 14
     for _, tot in res:
         assert tot == want
+
+
+def test_bler_point_single_active_user():
+    """`active = [1, 0]` (the 1-UE evaluation of results/nrx_rt_results): only the active transmitter's blocks count."""
+    from neural_rx_b200.bler import sim_point
+    cfg, grid, enc, dec, llr_fn = _bler_setup()
+    tot, first = sim_point(llr_fn, cfg, grid, enc, dec, point=0, ebno_db=6.0, num_slots=3, batch=2, keep_first=1, active=[1, 0])
+    assert tot["blocks"] == 3 and tot["bits"] == 3 * enc.tb_size and 0 <= tot["block_errors"] <= 3
+    assert np.array_equal(first[0][1], np.array([1, 0], np.float32))

@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--base-graph", default="auto", choices=("auto", "3gpp", "standin"))
     ap.add_argument("--target-block-errors", type=int, default=500)
     ap.add_argument("--check-oracle", type=int, default=0)
+    ap.add_argument("--active", type=int, nargs="+", default=None,
+                    help="transmitters that are on (e.g. 1 0: the single-UE evaluation of results/nrx_rt_results); default all")
     ap.add_argument("--num-it", type=int, nargs="+", default=None,
                     help="CGNN iterations to evaluate (num_it sweep of results/nrx_large_sweep_results); default: the cfg's")
     args = ap.parse_args()
@@ -82,7 +84,7 @@ def main():
     def run_point(pi, ebno):
         t0 = time.perf_counter()
         tot, first = sim_point(llr_fn, cfg, grid, enc, dec, pi, float(ebno), args.slots, args.batch, rank, world,
-                               args.target_block_errors, args.check_oracle)
+                               args.target_block_errors, args.check_oracle, args.active)
         if rank != 0:
             return
         dt = time.perf_counter() - t0
