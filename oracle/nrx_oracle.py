@@ -326,7 +326,7 @@ def positional_encoding(pilots: np.ndarray, pilot_mask: np.ndarray) -> np.ndarra
 
 def ls_channel_estimate(y: np.ndarray, pilots: np.ndarray, pilot_mask: np.ndarray,
                         num_cdm_groups_without_data: int = 2,
-                        nn_index: Optional[np.ndarray] = None) -> np.ndarray:
+                        nn_index: Optional[np.ndarray] = None, focc: bool = True) -> np.ndarray:
     """``PUSCHLSChannelEstimator(..., interpolation_type="nn")([y, no])`` followed by the slicing of
     ``NeuralPUSCHReceiver.estimate_channel`` (``copy_pytorch.py:899-911``).
 
@@ -335,7 +335,10 @@ def ls_channel_estimate(y: np.ndarray, pilots: np.ndarray, pilot_mask: np.ndarra
       2. FOCC / CDM de-spreading: mean of the two non-zero estimates in every block of
          2*num_cdm_groups_without_data pilot slots, kept only where the raw estimate is non-zero
          (in-tree twin ``utils/neural_rx.py:1620-1629``)
-      3. nearest-neighbour broadcast over the grid."""
+      3. nearest-neighbour broadcast over the grid.
+    ``focc=False`` skips step 2: that is the fork's own NumPy estimator ``MyLSChannelEstimatorNP``
+    (``utils/neural_rx.py:1129-1381``), against whose executed output steps 1 and 3 are pinned
+    (tests/golden/make_ref_ls_fixture.py)."""
     B, _, N, T, Fs = y.shape
     i_p, j_p = np.where(pilot_mask)
     yp = y[:, 0][:, :, i_p, j_p]                                             # [B, N, n_p]
@@ -349,10 +352,11 @@ def ls_channel_estimate(y: np.ndarray, pilots: np.ndarray, pilot_mask: np.ndarra
         nz = np.abs(p) > 0
         h = np.zeros_like(yp)
         h[..., nz] = yp[..., nz] / p[nz]
-        hb = h.reshape(B, N, -1, n)
-        cond = np.abs(hb) > 0
-        hs = np.repeat(hb.sum(axis=-1, keepdims=True) / 2.0, n, axis=-1)
-        h = np.where(cond, hs, 0).reshape(B, N, -1)
+        if focc:
+            hb = h.reshape(B, N, -1, n)
+            cond = np.abs(hb) > 0
+            hs = np.repeat(hb.sum(axis=-1, keepdims=True) / 2.0, n, axis=-1)
+            h = np.where(cond, hs, 0).reshape(B, N, -1)
         hg = h[..., nn_index[u]].reshape(B, N, T, Fs)                        # [B, N, T, F]
         hg = np.transpose(hg, (0, 3, 2, 1))                                  # [B, F, T, N]
         out[:, u] = np.concatenate([hg.real, hg.imag], axis=-1)

@@ -306,3 +306,20 @@ def test_positional_encoding_matches_reference_fragment():
     grid = build_grid(get_config("nrx_rt"), n_size_bwp=int(g["pe_prb"]))
     assert np.abs(O.positional_encoding(grid.pilots, grid.pilot_mask) - g["pe_ref"]).max() <= 1e-6
     assert np.abs(grid.pos_enc - g["pe_ref"]).max() <= 1e-6
+
+
+def test_ls_estimate_matches_reference_numpy_estimator():
+    """Pilot gather order, safe division and nearest-pilot broadcast of ``O.ls_channel_estimate`` against the
+    reference's own ``MyLSChannelEstimatorNP`` (utils/neural_rx.py:1129-1381) EXECUTED on a seeded 2-PRB batch
+    (tests/golden/make_ref_ls_fixture.py; slot 1 has an inactive user).  The fork's estimator has no FOCC
+    de-spreading, so the oracle runs with ``focc=False``; the FOCC step is pinned to ``_focc_removal`` above, and with
+    it switched on the estimate changes (the two steps are not accidentally the same thing)."""
+    g = np.load(os.path.join(GOLDEN, "ref_ls_fixture.npz"))
+    ref = g["h_hat"][:, 0, :, :, 0]                                   # [B, N, U, T, F] complex
+    ref = np.transpose(ref, (0, 2, 4, 3, 1))                          # [B, U, F, T, N]
+    ref = np.concatenate([ref.real, ref.imag], axis=-1)
+    got = O.ls_channel_estimate(g["y"], g["pilots"], g["pilot_mask"], focc=False)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 1e-6 * np.max(np.abs(ref))
+    with_focc = O.ls_channel_estimate(g["y"], g["pilots"], g["pilot_mask"])
+    assert np.max(np.abs(with_focc - ref)) > 1e-3
