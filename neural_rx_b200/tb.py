@@ -147,19 +147,23 @@ class BaseGraphUnavailable(RuntimeError):
 
 
 def _bg_csv_path(bg: int) -> Optional[str]:
+    """Path of the base-graph file: $NRX_LDPC_BG_DIR first, then the package data of an installed Sionna (0.x:
+    sionna/fec/ldpc/codes, 1.x: sionna/phy/fec/ldpc/codes) — located through the import machinery WITHOUT importing
+    Sionna (that would pull TensorFlow into a process that owns a GPU)."""
     name = f"5G_bg{bg}.csv"
     d = os.environ.get("NRX_LDPC_BG_DIR")
     if d and os.path.exists(os.path.join(d, name)):
         return os.path.join(d, name)
-    for mod in ("sionna.fec.ldpc.codes", "sionna.phy.fec.ldpc.codes"):
-        try:
-            import importlib
-            m = importlib.import_module(mod)
-            p = os.path.join(os.path.dirname(m.__file__), name)
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("sionna")
+    except (ImportError, ValueError):
+        spec = None
+    for root in (list(spec.submodule_search_locations or []) if spec is not None else []):
+        for sub in (("fec", "ldpc", "codes"), ("phy", "fec", "ldpc", "codes")):
+            p = os.path.join(root, *sub, name)
             if os.path.exists(p):
                 return p
-        except Exception:       # noqa: BLE001 - Sionna (and TensorFlow behind it) absent or broken: no tables
-            continue
     return None
 
 

@@ -221,3 +221,20 @@ def test_tb_size_matches_the_reference_notebook_printout():
     assert enc.num_coded_bits == 2304 and enc.coderate == 0.5400390625 and enc.tb_size == 1256
     assert TB.tb_size(4, 144, 4, 0.5400390625) == 1256
     assert np.array_equal(enc.scramble_seq[0], TB.gold_sequence((1 << 15) + 1, 2304))
+
+
+def test_base_graph_files_of_an_installed_sionna_are_found_without_importing_it(tmp_path, monkeypatch):
+    """A package named `sionna` on the path whose __init__ would raise if executed: its data file is still found."""
+    pkg = tmp_path / "sionna"
+    codes = pkg / "fec" / "ldpc" / "codes"
+    codes.mkdir(parents=True)
+    (pkg / "__init__.py").write_text("raise RuntimeError('sionna must not be imported by the TB chain')\n")
+    (codes / "5G_bg2.csv").write_text("x\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    monkeypatch.delenv("NRX_LDPC_BG_DIR", raising=False)
+    import importlib
+    importlib.invalidate_caches()
+    assert TB._bg_csv_path(2) == str(codes / "5G_bg2.csv")
+    assert TB._bg_csv_path(1) is None
+    import sys
+    assert "sionna" not in sys.modules
