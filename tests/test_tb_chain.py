@@ -2,6 +2,7 @@
 TBS rules, segmentation bookkeeping, LDPC encoding (H w = 0) on the structural stand-in base graphs, rate matching /
 interleaving / scrambling round trips, the BP decoder, and the loader for base-graph files in Sionna's layout."""
 import binascii
+import os
 
 import numpy as np
 import pytest
@@ -238,3 +239,26 @@ def test_base_graph_files_of_an_installed_sionna_are_found_without_importing_it(
     assert TB._bg_csv_path(1) is None
     import sys
     assert "sionna" not in sys.modules
+
+
+def test_published_curves_of_the_reference_decode():
+    """tests/golden/ref_published_curves.json = the reference's results/*_results decoded by tools/ref_results.py:
+    the nrx_large 2-UE BLER curve falls from ~1 at -2 dB to 0 at 6 dB, more CGNN iterations never hurt at 2 dB
+    (results/nrx_large_sweep_results), and the lookup used by tools/bler_sweep.py --published finds those points.  When
+    /root/reference is present the committed JSON must equal a fresh decode."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from tools import ref_results as R
+    pub = R.load_published()
+    c = pub["nrx_large_results"]
+    assert c["ebno_db"] == [float(e) for e in range(-2, 7)]
+    bler = c["bler"]["Neural Receiver|2|0"]
+    assert bler[0] > 0.99 and bler[-1] == 0.0 and all(a >= b for a, b in zip(bler, bler[1:]))
+    at2 = [R.published_at("nrx_large_sweep_results", f"Neural Receiver|2|0|{n}", 2.0) for n in range(1, 9)]
+    assert all(a >= b for a, b in zip(at2, at2[1:])) and abs(at2[0] - 0.41205) < 1e-9 and abs(at2[-1] - 0.15865) < 1e-9
+    assert R.published_at("nrx_large_results", "Neural Receiver|2|0", 2.5) is None
+    assert R.published_at("no_such_file", "x", 0.0) is None
+    ref_dir = "/root/reference/results"
+    if os.path.isdir(ref_dir):
+        assert {f: R.decode(os.path.join(ref_dir, f)) for f in sorted(os.listdir(ref_dir))} == pub

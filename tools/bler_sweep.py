@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--check-oracle", type=int, default=0)
     ap.add_argument("--active", type=int, nargs="+", default=None,
                     help="transmitters that are on (e.g. 1 0: the single-UE evaluation of results/nrx_rt_results); default all")
+    ap.add_argument("--published", default=None, metavar="RESULTS_FILE",
+                    help="print the reference's published BLER (tests/golden/ref_published_curves.json, e.g. nrx_large_results "
+                         "or nrx_large_sweep_results with --num-it) next to the measured one, for orientation")
     ap.add_argument("--num-it", type=int, nargs="+", default=None,
                     help="CGNN iterations to evaluate (num_it sweep of results/nrx_large_sweep_results); default: the cfg's")
     args = ap.parse_args()
@@ -102,6 +105,12 @@ def main():
                 e_g += int((~ok_g & (a > 0)).sum())
                 diff += int(((ok_o[0] != ok_g) & (a > 0)).sum())
             line += f"   {e_o:19d}  {e_g:19d}  {len(first) * U:12d}  {diff:16d}"
+        if args.published:
+            from tools.ref_results import published_at
+            n_on = int(sum(args.active)) if args.active else U
+            key = f"Neural Receiver|{n_on}|0" + (f"|{rx.num_it}" if "sweep" in args.published else "")
+            ref = published_at(args.published, key, float(ebno))
+            line += f"   published[{args.published}: {key}] " + ("n/a" if ref is None else f"{ref:.3e}")
         print(line, flush=True)
 
     for num_it in (args.num_it or [rx.num_it]):
